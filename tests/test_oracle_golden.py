@@ -1,0 +1,118 @@
+"""The oracle (oracle/) pinned against fixtures produced by the reference's own modules
+(tests/golden/make_golden.py).  CPU only."""
+import os
+
+import numpy as np
+import torch
+
+from icon_b200 import synthetic as S
+from oracle import engine as OE
+from oracle import query as OQ
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+def test_mlp_matches_reference_module(golden_dir):
+    g = _load(golden_dir, "mlp_index.npz")
+    for c0 in (13, 10):
+        sd = S.mlp_state_dict(c0=c0, seed=3)
+        y = OQ.mlp_forward(sd, torch.from_numpy(g[f"mlp{c0}_x"]))
+        assert np.abs(y.numpy() - g[f"mlp{c0}_y"]).max() <= 1e-6
+
+
+def test_index_and_orthogonal_match_reference(golden_dir):
+    g = _load(golden_dir, "mlp_index.npz")
+    o2 = OQ.index(torch.from_numpy(g["index2d_feat"]), torch.from_numpy(g["index2d_uv"]))
+    assert np.array_equal(o2.numpy(), g["index2d_out"])
+    o3 = OQ.index(torch.from_numpy(g["index3d_feat"]), torch.from_numpy(g["index3d_uv"]))
+    assert np.array_equal(o3.numpy(), g["index3d_out"])
+    oo = OQ.orthogonal(torch.from_numpy(g["ortho_pts"]), torch.from_numpy(g["ortho_calib"]))
+    assert np.array_equal(oo.numpy(), g["ortho_out"])
+
+
+def _field(points):
+    s = torch.tensor([0.45, 0.8, 0.3])
+    r = (points[0] / s).norm(dim=1)
+    bump = 0.15 * torch.sin(9.0 * points[0, :, 0]) * torch.cos(7.0 * points[0, :, 1])
+    return (0.5 + 2.0 * (0.8 - r) + bump).view(1, 1, -1)
+
+
+def test_engine_matches_reference_engine(golden_dir):
+    g = _load(golden_dir, "engine.npz")
+    for tag in ("a", "b"):
+        res = [int(r) for r in g[f"{tag}_res"]]
+        eng = OE.Seg3dOracle([[-1.0, 1.0, -1.0]], [[1.0, -1.0, 1.0]], res)
+        calls = []
+
+        def q(p):
+            calls.append(p.clone())
+            return _field(p)
+
+        occ = eng.forward(q)
+        assert len(calls) == int(g[f"{tag}_ncalls"])
+        for i, p in enumerate(calls):
+            assert np.array_equal(p.numpy(), g[f"{tag}_pts{i}"]), (tag, i)
+        # the analytic field's sin/norm are not bit-reproducible run to run (vectorisation);
+        # the engine itself adds no arithmetic beyond trilinear interpolation
+        assert np.abs(occ.numpy() - g[f"{tag}_occ"]).max() <= 2e-6
+
+
+def test_sdf_c_oracle_agrees_with_torch_transcription():
+    v, f = S.body_mesh(rings=10, segs=12, seed=1)
+    cm, vi = S.body_attributes(v)
+    verts, faces = torch.from_numpy(v)[None], torch.from_numpy(f)[None]
+    cmap, vis = torch.from_numpy(cm)[None], torch.from_numpy(vi)[None]
+    g = torch.Generator().manual_seed(0)
+    pts = torch.rand(1, 4000, 3, generator=g) * 2 - 1
+    a = OQ.cal_sdf_batch_c(verts, faces, cmap, vis, pts, return_face=True)
+    b = OQ.cal_sdf_batch_torch(verts, faces, cmap, vis, pts)
+    # distance and sign agree everywhere; the winning face agrees except on float-level ties
+    assert (a[0] - b[0]).abs().max() < 1e-6
+    same = a[4] == b[4]
+    assert same.float().mean() > 0.95
+    assert (a[1][0][same] - b[1][0][same]).abs().max() < 1e-4
+    assert (a[2][0][same] - b[2][0][same]).abs().max() < 1e-4
+    assert (a[3][0][same] == b[3][0][same]).float().mean() > 0.999
+
+
+def test_sdf_known_answer_sphere():
+    """Analytic known-answer: unit-ish sphere, distance / sign / normal direction."""
+    v, f = S.body_mesh(rings=40, segs=48, seed=0, extent=(0.6, 0.6, 0.6))
+    # make it an exact sphere of radius 0.6
+    v = (v / np.linalg.norm(v, axis=1, keepdims=True) * 0.6).astype(np.float32)
+    cm, vi = S.body_attributes(v)
+    g = torch.Generator().manual_seed(2)
+    pts = torch.rand(1, 3000, 3, generator=g) * 2 - 1
+    sdf, norm, _, _ = OQ.cal_sdf_batch_c(torch.from_numpy(v)[None], torch.from_numpy(f)[None],
+                                         torch.from_numpy(cm)[None], torch.from_numpy(vi)[None], pts)
+    r = pts[0].norm(dim=1)
+    expect = (0.6 - r) / np.sqrt(3.0)             # inside positive, divided by sqrt(3)
+    assert (sdf[0, :, 0] - expect).abs().max() < 2e-3       # faceting error of the polyhedron
+    assert ((sdf[0, :, 0] > 0) == (r < 0.6)).float().mean() > 0.995
+    # normal = interpolated outward vertex normal * (-1, 1, -1)
+    n = norm[0] * torch.tensor([-1.0, 1.0, -1.0])
+    cos = (n * pts[0] / r[:, None]).sum(1) / n.norm(dim=1)
+    assert cos.min() > 0.98
+
+
+def test_outlier_cmap_rule_is_order_dependent():
+    """k-th outlier's channel c receives s[(3k+c) mod K]."""
+    sdf = torch.tensor([[[0.2], [0.01], [-0.3], [0.4], [-0.02], [-0.5]]])
+    cmap = torch.arange(18, dtype=torch.float32).view(1, 6, 3) / 100.0
+    out = sdf.abs().ge(0.05)
+    sdf2 = sdf.clone()
+    sdf2[out] = torch.sign(sdf2[out])
+    c2 = cmap.clone()
+    c2[out.repeat(1, 1, 3)] = sdf2[out].repeat(1, 1, 3)
+    s = sdf2[out]                # [1,-1,1,-1]
+    K = len(s)
+    k = 0
+    for i in range(6):
+        if out[0, i, 0]:
+            for c in range(3):
+                assert c2[0, i, c] == s[(3 * k + c) % K]
+            k += 1
+        else:
+            assert torch.equal(c2[0, i], cmap[0, i])
