@@ -1,0 +1,73 @@
+// Shared helpers for libicon_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/icon_b200.h"
+
+namespace icon {
+
+void set_error(const char *fmt, ...);
+void count_launch(int n = 1);
+
+#define ICON_CHECK_ARG(cond, ...)                 \
+    do {                                          \
+        if (!(cond)) {                            \
+            icon::set_error(__VA_ARGS__);         \
+            return ICON_EINVAL;                   \
+        }                                         \
+    } while (0)
+
+#define ICON_CUDA(expr)                                                              \
+    do {                                                                             \
+        cudaError_t _e = (expr);                                                     \
+        if (_e != cudaSuccess) {                                                     \
+            icon::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr,             \
+                            cudaGetErrorString(_e));                                 \
+            return ICON_ECUDA;                                                       \
+        }                                                                            \
+    } while (0)
+
+// after a kernel launch
+#define ICON_LAUNCHED()                 \
+    do {                                \
+        icon::count_launch();           \
+        ICON_CUDA(cudaGetLastError());  \
+    } while (0)
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// carve a workspace
+struct Carver {
+    char *base;
+    size_t off;
+    explicit Carver(void *p) : base((char *)p), off(0) {}
+    template <typename T>
+    T *take(size_t n) {
+        off = align_up(off, 256);
+        T *r = (T *)(base ? base + off : nullptr);
+        off += n * sizeof(T);
+        return r;
+    }
+    size_t total() const { return align_up(off, 256); }
+};
+
+// ---------------------------------------------------------------- mesh workspace layout
+struct MeshView {
+    const float4 *tri;    // [F][3]: (a.xyz, ab.x) (ab.yz, ac.xy) (ac.z, -, -, -)
+    const float4 *sph;    // [F]: bounding sphere (centre xyz, radius), conservative
+    const float4 *attr;   // [F][6]: normals 9, cmap 9, vis 3, pad 3
+    const float4 *rbox;   // [F][2]: (ymin, ymax, zmin, zmax) (xmax, -, -, -)
+    float *vnormals;      // [V][3] scratch
+    int V, F;
+};
+size_t mesh_ws_bytes(int V, int F);
+MeshView mesh_view(const void *ws, int V, int F);
+
+// exclusive scan of int32 -> int64 totals; in/out may alias.  ws: scan_ws_bytes(n).
+size_t scan_ws_bytes(int64_t n);
+int scan_exclusive_i32(const int32_t *in, int32_t *out, int64_t n, int64_t *d_total /*may be null*/,
+                       void *ws, cudaStream_t stream);
+
+}  // namespace icon

@@ -1,0 +1,101 @@
+"""Coarse-to-fine reconstruction engine + mesh extraction, device resident.
+
+Mirror of `lib/common/seg3d_lossless.py::Seg3dLossless` (reference :36-604) for the one live
+mode (`faster=True`, `align_corners=True`, batch 1, 1 channel): same constructor, same
+`forward(**kwargs)` -> occupancy [R,R,R] or None, same `export_mesh(occ)` -> (verts, faces)
+on the CPU.  Per level the reference's interpolate x2 / conv3d / nonzero / unique / scatter_
+chain becomes: icon_grid_upsample -> icon_grid_dilate -> icon_grid_compact -> query_func ->
+icon_grid_scatter, with ONE host read-back per level (the number of boundary voxels, needed to
+shape the points tensor handed to query_func) instead of the reference's 4-6 syncs.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+
+
+class Seg3dLossless(nn.Module):
+    def __init__(self, query_func, b_min, b_max, resolutions, channels=1, balance_value=0.5,
+                 align_corners=False, visualize=False, debug=False, use_cuda_impl=False, faster=False,
+                 use_shadow=False, **kwargs):
+        super().__init__()
+        self.query_func = query_func
+        self.register_buffer("b_min", torch.tensor(b_min).float().unsqueeze(1))   # [1,1,3]
+        self.register_buffer("b_max", torch.tensor(b_max).float().unsqueeze(1))
+        if type(resolutions[0]) is int or np.isscalar(resolutions[0]):
+            resolutions = torch.tensor([(int(r), int(r), int(r)) for r in resolutions])
+        else:
+            resolutions = torch.tensor(resolutions)
+        self.register_buffer("resolutions", resolutions)
+        self.batchsize = self.b_min.size(0)
+        assert self.batchsize == 1
+        self.balance_value = balance_value
+        self.channels = channels
+        assert self.channels == 1
+        self.align_corners = align_corners
+        self.visualize = visualize
+        self.debug = debug
+        self.use_cuda_impl = use_cuda_impl
+        self.faster = faster
+        self.use_shadow = use_shadow
+        res = [int(r[0]) for r in resolutions]
+        for r in resolutions:
+            assert r[0] % 2 == 1 and r[1] % 2 == 1, f"resolution {r} need to be odd becuase of align_corner."
+            assert int(r[0]) == int(r[1]) == int(r[2]), "cubic grids only"
+        for a, b in zip(res[:-1], res[1:]):
+            assert b == 2 * a - 1, "each level must double the previous one (2^k+1 ladder, apps/ICON.py:62-72)"
+        self._res = res
+        self._bmin = [float(v) for v in self.b_min.reshape(-1)]
+        self._bmax = [float(v) for v in self.b_max.reshape(-1)]
+        self.last_query_counts = []          # points evaluated per query call of the last forward()
+
+    def forward(self, **kwargs):
+        if not (self.faster and self.align_corners):
+            raise NotImplementedError(
+                "only faster=True, align_corners=True is live in the reference (apps/ICON.py:78-90); "
+                "the lossless branch raises IndexError upstream (SURVEY.md section 4)")
+        return self._forward_faster(**kwargs)
+
+    def batch_eval_points(self, points, **kwargs):
+        occ = self.query_func(**kwargs, points=points)
+        if type(occ) is list:
+            occ = torch.stack(occ)
+        assert len(occ.size()) == 3, "query_func should return a occupancy with shape of [bz, C, N]"
+        return occ
+
+    def _forward_faster(self, **kwargs):
+        """seg3d_lossless.py:152-265."""
+        dev = self.b_min.device
+        res, R_last = self._res, self._res[-1]
+        self.last_query_counts = []
+        occ = None
+        done = None
+        for level, R in enumerate(res):
+            if level == 0:
+                pts = ops.grid_init_points(R, R_last, self._bmin, self._bmax, dev)
+                occ = self.batch_eval_points(pts, **kwargs).reshape(R, R, R).float().contiguous()
+                self.last_query_counts.append(R ** 3)
+                if ops.grid_count_above(occ, 0.5) == 0:        # :173-177
+                    return None
+            elif level == len(res) - 1:
+                occ, _, _ = ops.grid_upsample(occ, None, self.balance_value, want_mask=False)   # :186-203
+            else:
+                occ, boundary, done = ops.grid_upsample(occ, done, self.balance_value)
+                k = 9 if level == 1 else (7 if level == 2 else 3)                              # :226-234
+                mask_xyz = ops.grid_dilate(boundary, k)
+                pts, idx = ops.grid_compact(mask_xyz, done, R_last, self._bmin, self._bmax)
+                if pts.shape[1] == 0:                                                          # :250-251
+                    continue
+                vals = self.batch_eval_points(pts, **kwargs)
+                self.last_query_counts.append(pts.shape[1])
+                ops.grid_scatter(occ, idx, vals)
+        return occ
+
+    def export_mesh(self, occupancys):
+        """seg3d_lossless.py:583-604: marching cubes at balance_value; returns CPU tensors."""
+        verts, faces = ops.marching_cubes(occupancys, self.balance_value)
+        return verts.cpu(), faces.cpu()
+
+    def display(self, sdf):
+        raise NotImplementedError("training-time preview (seg3d_lossless.py:566-581) is off the inference path")

@@ -1,0 +1,286 @@
+"""Host-side mirror of the reference's lib/net API for the occupancy-query path.
+
+Same class names, constructor arguments, method signatures and state_dict keys as the
+reference so that apps/ICON.py / apps/infer.py and `load_checkpoint`
+(lib/dataset/mesh_util.py:187-237) work unchanged; the bodies call the sm_100a kernels in
+libicon_b200.so through icon_b200.ops.  Re-exported under the reference's import paths by
+lib/net/*.py and lib/common/train_util.py.
+
+  MLP            lib/net/MLP.py:8-72
+  BasePIFuNet    lib/net/BasePIFuNet.py:23-84
+  HGPIFuNet      lib/net/HGPIFuNet.py:34-410   (filter / query / get_normal; eval path)
+  query_func     lib/common/train_util.py:324-348
+"""
+import torch
+import torch.nn as nn
+
+from . import ops
+from .encoders import HGFilter, NormalNet, VolumeEncoder
+
+
+def _tensor_key(*tensors):
+    return tuple((t.data_ptr(), t._version, tuple(t.shape), str(t.device)) for t in tensors)
+
+
+def init_net(net, init_gain=0.02):
+    """lib/net/net_util.py:73-126 with the defaults every caller uses (xavier-normal, gain .02)."""
+    def init_func(m):
+        classname = m.__class__.__name__
+        if hasattr(m, "weight") and (classname.find("Conv") != -1 or classname.find("Linear") != -1):
+            nn.init.xavier_normal_(m.weight.data, gain=init_gain)
+            if getattr(m, "bias", None) is not None:
+                nn.init.constant_(m.bias.data, 0.0)
+        elif classname.find("BatchNorm2d") != -1:
+            nn.init.normal_(m.weight.data, 1.0, init_gain)
+            nn.init.constant_(m.bias.data, 0.0)
+    net.apply(init_func)
+    return net
+
+
+class MLP(nn.Module):
+    """Occupancy MLP.  Parameters live in the same Conv1d / BatchNorm1d containers as the
+    reference (identical state_dict); forward runs the fused kernel on BN-folded, packed weights."""
+
+    def __init__(self, filter_channels, name=None, res_layers=[], norm="group", last_op=None):
+        super().__init__()
+        self.filters = nn.ModuleList()
+        self.norms = nn.ModuleList()
+        self.res_layers = res_layers
+        self.norm = norm
+        self.last_op = last_op
+        self.name = name
+        self.filter_channels = list(filter_channels)
+        for l in range(0, len(filter_channels) - 1):
+            cin = filter_channels[l] + (filter_channels[0] if l in self.res_layers else 0)
+            self.filters.append(nn.Conv1d(cin, filter_channels[l + 1], 1))
+            if l != len(filter_channels) - 2:
+                if norm == "group":
+                    self.norms.append(nn.GroupNorm(32, filter_channels[l + 1]))
+                elif norm == "batch":
+                    self.norms.append(nn.BatchNorm1d(filter_channels[l + 1]))
+                elif norm == "instance":
+                    self.norms.append(nn.InstanceNorm1d(filter_channels[l + 1]))
+                elif norm == "weight":
+                    self.filters[l] = nn.utils.weight_norm(self.filters[l], name="weight")
+        self._packed = None
+        self._packed_key = None
+
+    @property
+    def c0(self):
+        return self.filter_channels[0]
+
+    def packed(self):
+        """BN-folded k-major weight block on the module's device (cached on tensor versions)."""
+        if self.norm != "batch":
+            raise NotImplementedError("fused MLP kernel supports norm_mlp='batch' only (all shipped configs)")
+        if self.training:
+            raise NotImplementedError("fused MLP kernel is inference-only (BatchNorm1d in eval mode)")
+        sd = self.state_dict()
+        key = _tensor_key(*[sd[k] for k in sorted(sd)])
+        if self._packed is None or key != self._packed_key:
+            dev = self.filters[0].weight.device
+            self._packed = ops.pack_mlp(sd, self.c0, device=dev)
+            self._packed_key = key
+        return self._packed
+
+    def forward(self, feature):
+        """feature [1, C_in, N] -> [1, 1, N]"""
+        if feature.shape[0] != 1:
+            raise NotImplementedError("fused MLP kernel: B=1 (inference path)")
+        y = ops.mlp_only(feature, self.packed(), self.c0)
+        if self.last_op is not None:
+            y = self.last_op(y)
+        return y
+
+
+class BasePIFuNet(nn.Module):
+    def __init__(self, projection_mode="orthogonal", error_term=nn.MSELoss()):
+        super().__init__()
+        self.name = "base"
+        self.error_term = error_term
+        if projection_mode != "orthogonal":
+            raise NotImplementedError("only projection_mode='orthogonal' is on the hot path (config.py:33)")
+        self.projection_mode = projection_mode
+
+    def filter(self, images):
+        return None
+
+    def query(self, features, points, calibs, transforms=None):
+        return None
+
+    def get_error(self, preds, labels):
+        return self.error_term(preds, labels)
+
+
+class HGPIFuNet(BasePIFuNet):
+    """lib/net/HGPIFuNet.py:34-410, inference path (eval mode, B=1)."""
+
+    def __init__(self, cfg, projection_mode="orthogonal", error_term=nn.MSELoss()):
+        super().__init__(projection_mode=projection_mode, error_term=error_term)
+        self.l1_loss = nn.SmoothL1Loss()
+        self.opt = cfg.net
+        self.root = getattr(cfg, "root", "./data/")
+        self.overfit = getattr(cfg, "overfit", False)
+        channels_IF = list(self.opt.mlp_dim)
+        self.use_filter = self.opt.use_filter
+        self.prior_type = self.opt.prior_type
+        self.smpl_feats = list(getattr(self.opt, "smpl_feats", []))
+        self.smpl_dim = getattr(self.opt, "smpl_dim", 3)
+        self.voxel_dim = getattr(self.opt, "voxel_dim", 32)
+        self.hourglass_dim = self.opt.hourglass_dim
+        self.sdf_clip = cfg.sdf_clip / 100.0
+        self.in_geo = [item[0] for item in self.opt.in_geo]
+        self.in_nml = [item[0] for item in self.opt.in_nml]
+        self.in_geo_dim = sum([item[1] for item in self.opt.in_geo])
+        self.in_nml_dim = sum([item[1] for item in self.opt.in_nml])
+        self.in_total = self.in_geo + self.in_nml
+        self.smpl_feat_dict = None
+
+        if self.prior_type == "icon":
+            if "image" in self.in_geo:
+                self.channels_filter = [[0, 1, 2, 3, 4, 5], [0, 1, 2, 6, 7, 8]]
+            else:
+                self.channels_filter = [[0, 1, 2], [3, 4, 5]]
+        else:
+            if "image" in self.in_geo:
+                self.channels_filter = [[0, 1, 2, 3, 4, 5, 6, 7, 8]]
+            else:
+                self.channels_filter = [[0, 1, 2, 3, 4, 5]]
+
+        channels_IF[0] = self.hourglass_dim if self.use_filter else len(self.channels_filter[0])
+        if self.prior_type == "icon" and "vis" not in self.smpl_feats:
+            channels_IF[0] += self.hourglass_dim if self.use_filter else len(self.channels_filter[0])
+        if self.prior_type == "icon":
+            channels_IF[0] += self.smpl_dim
+        elif self.prior_type == "pamir":
+            channels_IF[0] += self.voxel_dim
+            self.ve = VolumeEncoder(3, self.voxel_dim, self.opt.num_stack)
+        else:
+            channels_IF[0] += 1
+
+        self.icon_keys = ["smpl_verts", "smpl_faces", "smpl_vis", "smpl_cmap"]
+        self.pamir_keys = ["voxel_verts", "voxel_faces", "pad_v_num", "pad_f_num"]
+
+        self.if_regressor = MLP(filter_channels=channels_IF, name="if", res_layers=self.opt.res_layers,
+                                norm=self.opt.norm_mlp,
+                                last_op=nn.Sigmoid() if not cfg.test_mode else None)
+        if self.use_filter:
+            if self.opt.gtype == "HGPIFuNet":
+                self.F_filter = HGFilter(self.opt, self.opt.num_stack, len(self.channels_filter[0]))
+            else:
+                raise NotImplementedError(f"Backbone {self.opt.gtype} is unimplemented")
+        self.normal_filter = NormalNet(cfg)
+        init_net(self)
+        self._body = None
+        self._body_key = None
+        self._vol_feat = None
+
+    # ------------------------------------------------------------------ filter
+    def get_normal(self, in_tensor_dict):
+        """HGPIFuNet.py:167-192."""
+        if (not self.training) and (not self.overfit):
+            with torch.no_grad():
+                feat_lst = []
+                if "image" in self.in_geo:
+                    feat_lst.append(in_tensor_dict["image"])
+                if "normal_F" in self.in_geo and "normal_B" in self.in_geo:
+                    if "normal_F" not in in_tensor_dict.keys() or "normal_B" not in in_tensor_dict.keys():
+                        (nmlF, nmlB) = self.normal_filter(in_tensor_dict)
+                    else:
+                        nmlF = in_tensor_dict["normal_F"]
+                        nmlB = in_tensor_dict["normal_B"]
+                    feat_lst.append(nmlF)
+                    feat_lst.append(nmlB)
+            in_filter = torch.cat(feat_lst, dim=1)
+        else:
+            in_filter = torch.cat([in_tensor_dict[key] for key in self.in_geo], dim=1)
+        return in_filter
+
+    def filter(self, in_tensor_dict, return_inter=False):
+        """HGPIFuNet.py:204-266: image / normal maps -> feature maps; caches the SMPL tensors."""
+        in_filter = self.get_normal(in_tensor_dict)
+        features_G = []
+        if self.prior_type == "icon":
+            if self.use_filter:
+                features_F = self.F_filter(in_filter[:, self.channels_filter[0]])
+                features_B = self.F_filter(in_filter[:, self.channels_filter[1]])
+            else:
+                features_F = [in_filter[:, self.channels_filter[0]]]
+                features_B = [in_filter[:, self.channels_filter[1]]]
+            for idx in range(len(features_F)):
+                features_G.append(torch.cat([features_F[idx], features_B[idx]], dim=1))
+        else:
+            if self.use_filter:
+                features_G = self.F_filter(in_filter[:, self.channels_filter[0]])
+            else:
+                features_G = [in_filter[:, self.channels_filter[0]]]
+
+        if self.prior_type == "icon":
+            self.smpl_feat_dict = {k: in_tensor_dict[k] for k in self.icon_keys}
+        elif self.prior_type == "pamir":
+            self.smpl_feat_dict = {k: in_tensor_dict[k] for k in self.pamir_keys if k in in_tensor_dict}
+            if "vol_feat" in in_tensor_dict:      # pre-encoded volume feature
+                self._vol_feat = in_tensor_dict["vol_feat"]
+        features_out = [features_G[-1]] if not self.training else features_G
+        if return_inter:
+            return features_out, in_filter
+        return features_out
+
+    # ------------------------------------------------------------------ query
+    def _prepared_body(self):
+        d = self.smpl_feat_dict
+        if d is None:
+            raise RuntimeError("HGPIFuNet.query (icon prior) needs filter() first: smpl_feat_dict is empty")
+        ts = [d[k] for k in self.icon_keys]
+        key = _tensor_key(*ts)
+        if self._body is None or key != self._body_key:
+            if d["smpl_verts"].shape[0] != 1:
+                raise NotImplementedError("B=1 on the inference path")
+            self._body = ops.SmplBody(d["smpl_verts"], d["smpl_faces"], d["smpl_cmap"], d["smpl_vis"])
+            self._body_key = key
+        return self._body
+
+    def query(self, features, points, calibs, transforms=None, regressor=None):
+        """HGPIFuNet.py:268-367.  points [1,3,N], calibs [1,4,4] -> [preds [1,1,N]]."""
+        if transforms is not None:
+            raise NotImplementedError("image-space `transforms` are never passed on the inference path")
+        if points.shape[0] != 1:
+            raise NotImplementedError("B=1 on the inference path (seg3d_lossless.py:73, train_util.py:330)")
+        regressor = regressor if regressor is not None else self.if_regressor
+        if self.prior_type == "icon" and set(self.smpl_feats) != {"sdf", "cmap", "norm", "vis"}:
+            raise NotImplementedError("fused query kernel implements smpl_feats = sdf, cmap, norm, vis")
+        preds_list = []
+        body = self._prepared_body() if self.prior_type == "icon" else None
+        vol = None
+        if self.prior_type == "pamir":
+            vol = self._vol_feat
+            if vol is None:
+                raise NotImplementedError("pamir prior: pass a pre-encoded in_tensor_dict['vol_feat'] "
+                                          "(voxelisation kernel: DESIGN.md 'next')")
+        with torch.no_grad():
+            for im_feat in features:
+                preds = ops.query(self.prior_type, points, calibs, im_feat, regressor.packed(), regressor.c0,
+                                  body=body, vol_feat=vol, sdf_clip=self.sdf_clip)
+                if regressor.last_op is not None:
+                    preds = regressor.last_op(preds)
+                preds_list.append(preds)
+        return preds_list
+
+    def forward(self, in_tensor_dict):
+        raise NotImplementedError("training forward (HGPIFuNet.py:389-410) is out of scope (SURVEY.md 8f rank 4)")
+
+
+def query_func(opt, netG, features, points, proj_matrix=None):
+    """lib/common/train_util.py:324-348.  points [1,N,3] -> preds [1,1,N]."""
+    assert len(points) == 1
+    samples = points.repeat(opt.num_views, 1, 1) if opt.num_views != 1 else points
+    samples = samples.permute(0, 2, 1)
+    if proj_matrix is not None:
+        # geometry.orthogonal folded into the kernel: pass the matrix as the calibration
+        calib_tensor = proj_matrix.float()
+    else:
+        calib_tensor = torch.eye(4, dtype=torch.float32)[None]
+    preds = netG.query(features=features, points=samples, calibs=calib_tensor, regressor=netG.if_regressor)
+    if type(preds) is list:
+        preds = preds[0]
+    return preds

@@ -1,0 +1,258 @@
+"""Tensor-level wrappers over the C ABI (include/icon_b200.h).
+
+PyTorch is plumbing here: device memory (caching allocator), the current CUDA stream and
+dtype/shape checks.  Every function enqueues hand-written sm_100a kernels from
+libicon_b200.so on torch's current stream and fails loudly otherwise.
+"""
+import ctypes
+
+import torch
+
+from . import _C
+from ._C import check, lib
+
+PRIOR_ID = {"icon": 0, "pifu": 1, "pamir": 2}
+MLP_PACKED_FLOATS = 16 * 512 + 512 + 512 * 256 + 256 + 272 * 128 + 128 + 144 + 1
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _C.IconError("icon_b200 ops need CUDA tensors: there is no CPU path")
+
+
+def _hf(vals):
+    vals = [float(v) for v in vals]
+    return (ctypes.c_float * len(vals))(*vals)
+
+
+def _calib_rows(calib):
+    """calibs [B,4,4] or [B,3,4] (B=1) -> 12 host floats, rows of [R|t]."""
+    c = calib.detach().reshape(-1, calib.shape[-2], calib.shape[-1])[0][:3, :4].float().cpu()
+    return _hf(c.reshape(-1).tolist())
+
+
+# --------------------------------------------------------------------------- body mesh
+class SmplBody:
+    """Device-side prepared SMPL body (icon_smpl_prepare): vertex normals, per-face records.
+
+    Replaces the per-call preamble of cal_sdf_batch (reference lib/dataset/mesh_util.py:367-372).
+    """
+
+    def __init__(self, verts, faces, cmap, vis):
+        _need_cuda(verts, faces, cmap, vis)
+        v = verts.detach().reshape(-1, 3).float().contiguous()
+        f = faces.detach().reshape(-1, 3).long().contiguous()
+        c = cmap.detach().reshape(-1, 3).float().contiguous()
+        s = vis.detach().reshape(-1).float().contiguous()
+        self.V, self.F = v.shape[0], f.shape[0]
+        if c.shape[0] != self.V or s.shape[0] != self.V:
+            raise _C.IconError("smpl_cmap / smpl_vis must have one row per vertex")
+        if self.F > 0 and (int(f.min()) < 0 or int(f.max()) >= self.V):
+            raise _C.IconError("smpl_faces index out of range")
+        nbytes = lib.icon_smpl_workspace_bytes(self.V, self.F)
+        self.ws = torch.empty(nbytes, dtype=torch.uint8, device=v.device)
+        check(lib.icon_smpl_prepare(_p(v), _p(f), _p(c), _p(s), self.V, self.F, _p(self.ws), nbytes, _stream()),
+              "icon_smpl_prepare")
+        self._keep = (v, f, c, s)
+
+
+# --------------------------------------------------------------------------- MLP packing
+def pack_mlp(sd, c0, prefix="", device=None):
+    """Fold BatchNorm1d(eval) into the 1x1 convs (lib/net/MLP.py:60-70) and pack k-major.
+
+    sd: state_dict with {prefix}filters.{l}.weight/bias and {prefix}norms.{l}.*; the kernel is
+    specialised for mlp_dim [c0,512,256,128,1], res_layers [2,3,4], norm 'batch'.
+    """
+    def g(k):
+        return sd[prefix + k].detach().double().cpu()
+
+    dims = []
+    l = 0
+    while prefix + f"filters.{l}.weight" in sd:
+        dims.append(tuple(sd[prefix + f"filters.{l}.weight"].shape[:2]))
+        l += 1
+    expect = [(512, c0), (256, 512), (128, 256 + c0), (1, 128 + c0)]
+    if dims != expect or c0 > 16:
+        raise NotImplementedError(
+            f"fused MLP kernel supports mlp_dim [c0<=16,512,256,128,1] with res_layers [2,3,4]; got {dims}")
+    Ws, bs = [], []
+    for l in range(4):
+        W = g(f"filters.{l}.weight")[:, :, 0]
+        b = g(f"filters.{l}.bias")
+        if l < 3:
+            if prefix + f"norms.{l}.running_mean" not in sd:
+                raise NotImplementedError("fused MLP kernel needs norm_mlp='batch' (eval-mode statistics)")
+            s = g(f"norms.{l}.weight") / torch.sqrt(g(f"norms.{l}.running_var") + 1e-5)
+            W = W * s[:, None]
+            b = (b - g(f"norms.{l}.running_mean")) * s + g(f"norms.{l}.bias")
+        Ws.append(W)
+        bs.append(b)
+    W0t = torch.zeros(16, 512, dtype=torch.float64)
+    W0t[:c0] = Ws[0].t()
+    W2t = torch.zeros(272, 128, dtype=torch.float64)
+    W2t[:256 + c0] = Ws[2].t()
+    W3 = torch.zeros(144, dtype=torch.float64)
+    W3[:128 + c0] = Ws[3][0]
+    packed = torch.cat([W0t.reshape(-1), bs[0], Ws[1].t().contiguous().reshape(-1), bs[1], W2t.reshape(-1), bs[2],
+                        W3, bs[3]]).float()
+    assert packed.numel() == MLP_PACKED_FLOATS
+    return packed.to(device) if device is not None else packed
+
+
+# --------------------------------------------------------------------------- query
+def _point_strides(points):
+    """points [1,3,N] (any strides) -> (tensor, stride_c, stride_n, N) in elements."""
+    if points.dim() != 3 or points.shape[0] != 1 or points.shape[1] != 3:
+        raise _C.IconError(f"points must be [1,3,N], got {tuple(points.shape)}")
+    if points.dtype != torch.float32:
+        points = points.float()
+    return points, points.stride(1), points.stride(2), points.shape[2]
+
+
+def query(prior, points, calib, feat, mlp_packed, c0, body=None, vol_feat=None, sdf_clip=0.05, out=None):
+    """Fused HGPIFuNet.query for one feature stack, B=1.  points [1,3,N] -> preds [1,1,N]."""
+    _need_cuda(points, feat, mlp_packed, vol_feat)
+    pts, sc, sn, N = _point_strides(points)
+    feat = feat.detach()
+    if feat.dim() != 4 or feat.shape[0] != 1:
+        raise _C.IconError(f"feature map must be [1,C,H,W], got {tuple(feat.shape)}")
+    feat = feat.float().contiguous()
+    C, H, W = feat.shape[1:]
+    pid = PRIOR_ID[prior]
+    if out is None:
+        out = torch.empty(1, 1, N, dtype=torch.float32, device=pts.device)
+    V = F = 0
+    mesh = None
+    if prior == "icon":
+        if body is None:
+            raise _C.IconError("icon prior needs a prepared SmplBody")
+        V, F, mesh = body.V, body.F, body.ws
+    VD = 0
+    if prior == "pamir":
+        vol_feat = vol_feat.detach().float().contiguous()
+        if vol_feat.dim() != 5 or vol_feat.shape[0] != 1 or vol_feat.shape[1] != 7 or \
+                not (vol_feat.shape[2] == vol_feat.shape[3] == vol_feat.shape[4]):
+            raise _C.IconError(f"vol_feat must be [1,7,D,D,D], got {tuple(vol_feat.shape)}")
+        VD = vol_feat.shape[2]
+    nbytes = lib.icon_query_workspace_bytes(N, F, pid)
+    ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=pts.device)
+    check(lib.icon_query(pid, _p(pts), sc, sn, N, _calib_rows(calib), _p(feat), C, H, W, _p(vol_feat), VD,
+                         _p(mesh), V, F, _p(mlp_packed), c0, float(sdf_clip), _p(out), _p(ws), nbytes, _stream()),
+          "icon_query")
+    return out
+
+
+def sdf_only(points, calib, body, brute=False):
+    """cal_sdf_batch outputs before the outlier rule: rec [N,8], face [N] (parity tap)."""
+    _need_cuda(points)
+    pts, sc, sn, N = _point_strides(points)
+    rec = torch.empty(N, 8, dtype=torch.float32, device=pts.device)
+    face = torch.empty(N, dtype=torch.int32, device=pts.device)
+    if brute:
+        check(lib.icon_sdf_bruteforce(_p(pts), sc, sn, N, _calib_rows(calib), _p(body.ws), body.V, body.F, _p(rec),
+                                      _p(face), _stream()), "icon_sdf_bruteforce")
+    else:
+        nbytes = lib.icon_query_workspace_bytes(N, body.F, 0)
+        ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=pts.device)
+        check(lib.icon_sdf_only(_p(pts), sc, sn, N, _calib_rows(calib), _p(body.ws), body.V, body.F, _p(rec),
+                                _p(face), _p(ws), nbytes, _stream()), "icon_sdf_only")
+    return rec, face
+
+
+def mlp_only(feature, mlp_packed, c0):
+    """MLP.forward on a [1,c0,N] feature tensor -> [1,1,N] (parity tap)."""
+    _need_cuda(feature, mlp_packed)
+    f = feature.detach().float().contiguous()
+    N = f.shape[2]
+    out = torch.empty(1, 1, N, dtype=torch.float32, device=f.device)
+    check(lib.icon_mlp_only(_p(f), c0, N, _p(mlp_packed), _p(out), _stream()), "icon_mlp_only")
+    return out
+
+
+# --------------------------------------------------------------------------- engine grids
+def grid_upsample(occ, done, balance, want_mask=True):
+    """[R,R,R] -> [2R-1]^3 trilinear (align_corners) + boundary mask + carried `done` set."""
+    R = occ.shape[0]
+    Ro = 2 * R - 1
+    out = torch.empty(Ro, Ro, Ro, dtype=torch.float32, device=occ.device)
+    boundary = torch.empty(Ro, Ro, Ro, dtype=torch.uint8, device=occ.device) if want_mask else None
+    done_out = torch.empty(Ro, Ro, Ro, dtype=torch.uint8, device=occ.device) if want_mask else None
+    check(lib.icon_grid_upsample(_p(occ), _p(done), R, float(balance), _p(out), _p(boundary), _p(done_out),
+                                 _stream()), "icon_grid_upsample")
+    return out, boundary, done_out
+
+
+def grid_dilate(mask, k):
+    R = mask.shape[0]
+    tmp = torch.empty_like(mask)
+    out = torch.empty_like(mask)
+    check(lib.icon_grid_dilate(_p(mask), R, k, _p(tmp), _p(out), _stream()), "icon_grid_dilate")
+    return out          # transposed: [x][y][z]
+
+
+def grid_compact(mask_xyz, done, R_last, b_min, b_max):
+    """-> (points [1,n,3] f32, indices [n] i64); one host sync to learn n."""
+    R = mask_xyz.shape[0]
+    dev = mask_xyz.device
+    n_all = R * R * R
+    nbytes = lib.icon_compact_workspace_bytes(R)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    pts = torch.empty(n_all, 3, dtype=torch.float32, device=dev)
+    idx = torch.empty(n_all, dtype=torch.int64, device=dev)
+    cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+    check(lib.icon_grid_compact(_p(mask_xyz), _p(done), R, R_last, _hf(b_min), _hf(b_max), _p(pts), _p(idx),
+                                n_all, _p(cnt), _p(ws), nbytes, _stream()), "icon_grid_compact")
+    n = int(cnt.item())
+    return pts[:n].unsqueeze(0), idx[:n]
+
+
+def grid_scatter(occ, indices, values):
+    n = indices.numel()
+    v = values.detach().reshape(-1).float().contiguous()
+    if v.numel() != n:
+        raise _C.IconError("grid_scatter: values / indices size mismatch")
+    check(lib.icon_grid_scatter(_p(occ), _p(indices), _p(v), n, _stream()), "icon_grid_scatter")
+
+
+def grid_init_points(R0, R_last, b_min, b_max, device):
+    pts = torch.empty(R0 ** 3, 3, dtype=torch.float32, device=device)
+    check(lib.icon_grid_init_points(R0, R_last, _hf(b_min), _hf(b_max), _p(pts), _stream()),
+          "icon_grid_init_points")
+    return pts.unsqueeze(0)
+
+
+def grid_count_above(occ, balance):
+    cnt = torch.zeros(1, dtype=torch.int64, device=occ.device)
+    o = occ.detach().float().contiguous()
+    check(lib.icon_grid_count_above(_p(o), o.numel(), float(balance), _p(cnt), _stream()), "icon_grid_count_above")
+    return int(cnt.item())
+
+
+# --------------------------------------------------------------------------- marching cubes
+def marching_cubes(occ, iso=0.5):
+    """export_mesh on the device: occ [R,R,R] -> (verts [Nv,3] f32|f64 xyz, faces [Nf,3] i64), CUDA."""
+    _need_cuda(occ)
+    o = occ.detach().float().contiguous()
+    R = o.shape[0]
+    if o.dim() != 3 or not (o.shape[1] == R and o.shape[2] == R):
+        raise _C.IconError(f"occupancy grid must be [R,R,R], got {tuple(o.shape)}")
+    padded = 0 if (R - 1) > 256 else 1           # seg3d_lossless.py:587: final.shape[0] > 256 -> PyMCubes branch
+    nbytes = lib.icon_mc_workspace_bytes(R, padded)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=o.device)
+    counts = torch.zeros(2, dtype=torch.int64, device=o.device)
+    check(lib.icon_mc_count(_p(o), R, float(iso), padded, _p(ws), nbytes, _p(counts), _stream()), "icon_mc_count")
+    nv, nt = [int(v) for v in counts.tolist()]
+    verts = torch.empty(nv, 3, dtype=torch.float32 if padded else torch.float64, device=o.device)
+    faces = torch.empty(nt, 3, dtype=torch.int64, device=o.device)
+    check(lib.icon_mc_emit(_p(o), R, float(iso), padded, _p(ws), _p(verts), _p(faces), nv, nt, _stream()),
+          "icon_mc_emit")
+    return verts, faces

@@ -1,0 +1,158 @@
+/*
+ * icon_b200.h -- C ABI of libicon_b200.so (sm_100a kernels for ICON's occupancy-query +
+ * mesh-extraction hot path).
+ *
+ * The reference (YuliangXiu/ICON) has no FFI: its "plugin API" for this path is Python
+ * nn.Module duck typing.  The Python mirror in icon_b200/ (re-exported under
+ * the reference's import paths in lib/) keeps those signatures and calls the entry points
+ * below through ctypes with raw device pointers.  Each entry point cites the reference
+ * code it replaces.  Conventions:
+ *
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless named h_*;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing
+ *     synchronises unless stated;
+ *   - no hidden allocation: the caller (torch's caching allocator) provides outputs and
+ *     workspaces; *_workspace_bytes() tell how much;
+ *   - return 0 on success, a negative ICON_E* code otherwise; icon_last_error() gives the
+ *     message (thread local).  There is no CPU fallback anywhere.
+ */
+#ifndef ICON_B200_H
+#define ICON_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ICON_OK 0
+#define ICON_EINVAL (-1)   /* bad argument / unsupported size */
+#define ICON_ECUDA (-2)    /* CUDA runtime error (message has the cudaError string) */
+#define ICON_ENOSPC (-3)   /* workspace or output buffer too small */
+
+#define ICON_PRIOR_ICON 0
+#define ICON_PRIOR_PIFU 1
+#define ICON_PRIOR_PAMIR 2
+
+typedef void *icon_stream_t;
+
+int icon_version(void);
+const char *icon_last_error(void);
+/* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
+int64_t icon_launch_count(void);
+
+/* ------------------------------------------------------------------ SMPL body preparation
+ * Replaces the per-call preamble of cal_sdf_batch, lib/dataset/mesh_util.py:367-372:
+ * pytorch3d Meshes.verts_normals_padded (area-weighted vertex normals, deterministic
+ * sequential-index_add order) and the four face_vertices gathers
+ * (lib/common/render_utils.py:149-163).  Builds, into `mesh_ws`, per-face records
+ * (a, ab, ac, bounding sphere), per-face attribute records (normals, cmap, vis at the three
+ * corners) and the +x-ray culling boxes.  Done once per body, not once per query.
+ * verts [V,3] f32, faces [F,3] i64, cmap [V,3] f32, vis [V] f32 (0/1). */
+size_t icon_smpl_workspace_bytes(int V, int F);
+int icon_smpl_prepare(const float *verts, const int64_t *faces, const float *cmap,
+                      const float *vis, int V, int F, void *mesh_ws, size_t mesh_ws_bytes,
+                      icon_stream_t stream);
+
+/* ------------------------------------------------------------------ occupancy MLP weights
+ * Replaces MLP.__init__/forward's per-layer Conv1d + BatchNorm1d(eval) (lib/net/MLP.py:26-72):
+ * the host folds BN into the 1x1 convs and packs the layers; this copies nothing, it only
+ * describes the packed device buffer so the kernels can check it.
+ * Packed layout (floats): W0t [16][512] | b0 [512] | W1t [512][256] | b1 [256] |
+ *                         W2t [272][128] | b2 [128] | W3 [144] | b3 [1]
+ * with k-major ("t") storage, the c0 input channels zero-padded to 16, and skip-concat
+ * columns ordered [y | x0]. */
+#define ICON_MLP_PACKED_FLOATS (16 * 512 + 512 + 512 * 256 + 256 + 272 * 128 + 128 + 144 + 1)
+
+/* ------------------------------------------------------------------ fused occupancy query
+ * Replaces HGPIFuNet.query (lib/net/HGPIFuNet.py:268-367) + cal_sdf_batch
+ * (lib/dataset/mesh_util.py:357-396; kaolin point_to_mesh_distance / check_sign) +
+ * geometry.index / orthogonal (lib/net/geometry.py:21-61) + feat_select
+ * (mesh_util.py:266-277) + MLP.forward (lib/net/MLP.py:49-72) for one feature stack, B=1.
+ *
+ *   points      : xyz of point i at points[c*stride_c + i*stride_n], c in 0..2
+ *   calib       : HOST pointer to 12 floats, rows of [R|t] (calibs[0,:3,:4])
+ *   feat        : image feature map [C,H,W] f32 (C = 12 or 6 for icon, 12 pifu, 6 pamir)
+ *   vol_feat    : pamir only: [7,D,D,D] f32; else NULL
+ *   mesh_ws     : icon only: workspace filled by icon_smpl_prepare (same V,F); else NULL
+ *   mlp_packed  : ICON_MLP_PACKED_FLOATS floats
+ *   c0          : MLP input channels (13 or 10)
+ *   sdf_clip    : cfg.sdf_clip/100 (icon)
+ *   out         : [N] f32 occupancy (preds[0,0,:])
+ *   ws          : scratch, icon_query_workspace_bytes(N, F) bytes
+ */
+size_t icon_query_workspace_bytes(int64_t N, int F, int prior);
+int icon_query(int prior, const float *points, int64_t stride_c, int64_t stride_n, int64_t N,
+               const float *h_calib, const float *feat, int C, int H, int W,
+               const float *vol_feat, int VD, const void *mesh_ws, int V, int F,
+               const float *mlp_packed, int c0, float sdf_clip, float *out, void *ws,
+               size_t ws_bytes, icon_stream_t stream);
+
+/* Debug / parity tap: the SMPL block alone (cal_sdf_batch outputs before the outlier rule).
+ * rec [N,8] f32 = sdf, cmap xyz, norm xyz, vis(0/1); face [N] i32 nearest face id. */
+int icon_sdf_only(const float *points, int64_t stride_c, int64_t stride_n, int64_t N,
+                  const float *h_calib, const void *mesh_ws, int V, int F, float *rec,
+                  int32_t *face, void *ws, size_t ws_bytes, icon_stream_t stream);
+/* Same outputs by brute force over all faces (no bricks); slow, for cross-checks. */
+int icon_sdf_bruteforce(const float *points, int64_t stride_c, int64_t stride_n, int64_t N,
+                        const float *h_calib, const void *mesh_ws, int V, int F, float *rec,
+                        int32_t *face, icon_stream_t stream);
+/* MLP alone on a ready [c0,N] feature matrix (parity tap for lib/net/MLP.py:49-72). */
+int icon_mlp_only(const float *feature, int c0, int64_t N, const float *mlp_packed, float *out,
+                  icon_stream_t stream);
+
+/* ------------------------------------------------------------------ reconstruction engine
+ * Replace the per-level body of Seg3dLossless._forward_faster
+ * (lib/common/seg3d_lossless.py:186-263).  Grids are [R,R,R] indexed [z][y][x]. */
+
+/* seg3d_lossless.py:190-223: both F.interpolate(trilinear, align_corners=True) calls
+ * (occupancy and (occ>balance) mask) fused with is_boundary = 0<valid<1 and with the
+ * carry-over of the already-evaluated set (coords_accum*2).  R_out = 2*R_in-1.
+ * boundary/done_out may be NULL (last level: upsample only, :186-203). */
+int icon_grid_upsample(const float *occ_in, const uint8_t *done_in, int R_in, float balance,
+                       float *occ_out, uint8_t *boundary, uint8_t *done_out,
+                       icon_stream_t stream);
+/* seg3d_lossless.py:226-234 + seg3d_utils.py:169-181: (SmoothConv3D(k)(mask) > 0) == binary
+ * dilation by a k^3 box; separable.  tmp: R^3 bytes.  The result is written TRANSPOSED,
+ * out_xyz[x][y][z], which is the order `is_boundary.permute(2,1,0).nonzero()` walks. */
+int icon_grid_dilate(const uint8_t *mask, int R, int k, uint8_t *tmp, uint8_t *out_xyz,
+                     icon_stream_t stream);
+/* seg3d_lossless.py:236-249 + batch_eval :125-138: clear already-evaluated voxels, stable
+ * compaction in (x,y,z)-lexicographic order, emit query points
+ * p = c*stride/(R_last-1)*(b_max-b_min)+b_min and linear indices z*R*R+y*R+x; marks the
+ * selected voxels in `done`.  *d_count (device int64) receives n.  ws: icon_compact_workspace_bytes(R). */
+size_t icon_compact_workspace_bytes(int R);
+int icon_grid_compact(const uint8_t *mask_xyz, uint8_t *done, int R, int R_last,
+                      const float *h_bmin, const float *h_bmax, float *points, int64_t *indices,
+                      int64_t capacity, int64_t *d_count, void *ws, size_t ws_bytes,
+                      icon_stream_t stream);
+/* seg3d_lossless.py:255-258: occupancys.scatter_(2, point_indices, occupancys_topk). */
+int icon_grid_scatter(float *occ, const int64_t *indices, const float *values, int64_t n,
+                      icon_stream_t stream);
+/* seg3d_lossless.py:168-177: level-0 lattice points (create_grid3D + batch_eval) and the
+ * "(occupancys > 0.5).sum() == 0" test (d_count receives the number above balance). */
+int icon_grid_init_points(int R0, int R_last, const float *h_bmin, const float *h_bmax,
+                          float *points, icon_stream_t stream);
+int icon_grid_count_above(const float *occ, int64_t n, float balance, int64_t *d_count,
+                          icon_stream_t stream);
+
+/* ------------------------------------------------------------------ marching cubes
+ * Replaces Seg3dLossless.export_mesh (lib/common/seg3d_lossless.py:583-604): kaolin
+ * voxelgrids_to_trianglemeshes (<=256^3) / PyMCubes (>256^3) at iso `balance`, including the
+ * occupancys[1:,1:,1:] crop and the [:, [2,1,0]] / [:, [0,2,1]] permutations.  Indexing
+ * contract: DESIGN.md "marching cubes" (oracle/mcubes.py restates it).
+ *   occ [R,R,R]; padded=1 -> kaolin branch (zero pad, padded-frame coords, f32 verts),
+ *   padded=0 -> PyMCubes branch (f64 verts).
+ * icon_mc_count fills ws and writes {n_verts, n_tris} to d_counts (device int64[2]);
+ * icon_mc_emit writes verts [n_verts,3] (f32 or f64) and faces [n_tris,3] i64. */
+size_t icon_mc_workspace_bytes(int R, int padded);
+int icon_mc_count(const float *occ, int R, float iso, int padded, void *ws, size_t ws_bytes,
+                  int64_t *d_counts, icon_stream_t stream);
+int icon_mc_emit(const float *occ, int R, float iso, int padded, const void *ws, void *verts,
+                 int64_t *faces, int64_t n_verts, int64_t n_tris, icon_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

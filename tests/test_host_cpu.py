@@ -1,0 +1,140 @@
+"""Host-side logic that needs no GPU: C-ABI surface, weight packing, state_dict parity, configs."""
+import ctypes
+import json
+import os
+import re
+
+import pytest
+import torch
+
+from icon_b200 import synthetic as S
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built_lib():
+    from icon_b200 import build
+    return build.build()
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    hdr = open(os.path.join(ROOT, "include", "icon_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(icon_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 20
+    lib = ctypes.CDLL(built_lib)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/icon_b200.h but not exported"
+    from icon_b200 import _C
+    assert set(_C.EXPORTS) == declared          # the ctypes table covers the whole header
+    assert _C.lib.icon_version() == 1
+    # size queries are host-only and must work without a GPU
+    assert _C.lib.icon_smpl_workspace_bytes(6890, 13776) > 13776 * 64
+    assert _C.lib.icon_query_workspace_bytes(1 << 20, 13776, 0) > (1 << 20) * 32
+    assert _C.lib.icon_mc_workspace_bytes(257, 1) >= 258 ** 3 * 10
+
+
+def test_ops_refuse_cpu_tensors(built_lib):
+    from icon_b200 import _C, ops
+    sd = S.mlp_state_dict(13, seed=1)
+    packed = ops.pack_mlp(sd, 13)
+    with pytest.raises(_C.IconError):
+        ops.mlp_only(torch.zeros(1, 13, 8), packed, 13)      # no CPU fallback
+
+
+@pytest.mark.parametrize("c0", [13, 10])
+def test_pack_mlp_folding_matches_oracle(built_lib, c0):
+    """Unpack the BN-folded k-major block and evaluate it with plain matmuls on the CPU."""
+    from icon_b200 import ops
+    from oracle import query as OQ
+    sd = S.mlp_state_dict(c0, seed=4)
+    p = ops.pack_mlp(sd, c0).double()
+    o = 0
+
+    def take(n):
+        nonlocal o
+        r = p[o:o + n]
+        o += n
+        return r
+
+    W0t, b0 = take(16 * 512).view(16, 512), take(512)
+    W1t, b1 = take(512 * 256).view(512, 256), take(256)
+    W2t, b2 = take(272 * 128).view(272, 128), take(128)
+    W3, b3 = take(144), take(1)
+    assert o == ops.MLP_PACKED_FLOATS
+    x = torch.randn(1, c0, 500, generator=torch.Generator().manual_seed(0)).double()
+    x16 = torch.zeros(16, 500, dtype=torch.float64)
+    x16[:c0] = x[0]
+    lre = torch.nn.functional.leaky_relu
+    h0 = lre(W0t.t() @ x16 + b0[:, None], 0.01)
+    h1 = lre(W1t.t() @ h0 + b1[:, None], 0.01)
+    h2 = lre(W2t.t() @ torch.cat([h1, x16]) + b2[:, None], 0.01)
+    y = W3 @ torch.cat([h2, x16]) + b3
+    ref = OQ.mlp_forward(sd, x, dtype=torch.float64)[0, 0]
+    assert (y - ref).abs().max() < 1e-5
+
+
+def test_state_dict_keys_match_reference(golden_dir):
+    from icon_b200 import config, net
+    keys = json.load(open(os.path.join(golden_dir, "state_dict_keys.json")))
+
+    def shapes(m):
+        return {k: list(v.shape) for k, v in m.state_dict().items()}
+
+    g = net.HGPIFuNet(config.preset("icon-filter"))
+    assert shapes(g.F_filter) == keys["HGFilter(opt,2,3)"]
+    assert shapes(g.normal_filter.netF) == keys["define_G(6,3,64,global,4,9,1,3,instance)"]
+    assert shapes(g.normal_filter.netB) == keys["define_G(6,3,64,global,4,9,1,3,instance)"]
+    assert shapes(g.if_regressor) == keys["MLP([13,512,256,128,1])"]
+    p = net.HGPIFuNet(config.preset("pamir"))
+    assert shapes(p.ve) == keys["VolumeEncoder(3,7,2)"]
+    assert shapes(p.F_filter) == keys["HGFilter(opt,2,9)"]
+    top = set(k.split(".")[0] for k in g.state_dict())
+    assert top == {"if_regressor", "F_filter", "normal_filter"}
+
+
+@pytest.mark.parametrize("name,c0", [("icon-filter", 13), ("icon-nofilter", 10), ("pamir", 13), ("pifu", 13)])
+def test_presets_give_reference_mlp_width(name, c0):
+    from icon_b200 import config, net
+    g = net.HGPIFuNet(config.preset(name))
+    assert g.if_regressor.filter_channels == [c0, 512, 256, 128, 1]
+    assert g.sdf_clip == pytest.approx(0.05)
+    assert g.if_regressor.last_op is None          # test_mode: no sigmoid (HGPIFuNet.py:133)
+
+
+def test_drop_in_import_paths():
+    from lib.net import HGPIFuNet, NormalNet, VolumeEncoder, BasePIFuNet  # noqa: F401
+    from lib.net.MLP import MLP  # noqa: F401
+    from lib.net.HGFilters import HGFilter  # noqa: F401
+    from lib.common.seg3d_lossless import Seg3dLossless
+    from lib.common.train_util import query_func  # noqa: F401
+    eng = Seg3dLossless(query_func=None, b_min=[[-1.0, 1.0, -1.0]], b_max=[[1.0, -1.0, 1.0]],
+                        resolutions=[33, 65, 129, 257], align_corners=True, faster=True)
+    assert set(dict(eng.named_buffers())) >= {"b_min", "b_max", "resolutions"}
+    with pytest.raises(AssertionError):
+        Seg3dLossless(None, [[-1.0, 1, -1]], [[1.0, -1, 1]], resolutions=[32, 64])
+    with pytest.raises(NotImplementedError):
+        Seg3dLossless(None, [[-1.0, 1, -1]], [[1.0, -1, 1]], resolutions=[33, 65], faster=False)()
+
+
+def test_oracle_marching_cubes_is_watertight_and_matches_analytic_sphere():
+    import numpy as np
+    from oracle import mcubes as OM
+    R = 41
+    a = np.linspace(-1, 1, R)
+    z, y, x = np.meshgrid(a, a, a, indexing="ij")
+    occ = (0.5 + (0.6 - np.sqrt(x * x + y * y + z * z))).astype(np.float32)
+    v, f = OM.export_mesh(occ, 0.5)
+    e = np.concatenate([f[:, [0, 1]], f[:, [1, 2]], f[:, [2, 0]]])
+    _, c = np.unique(np.sort(e, 1), axis=0, return_counts=True)
+    assert (c == 2).all()
+    # vertices (grid-index units of the ORIGINAL grid) lie on the radius-0.6 sphere
+    p = v / ((R - 1) / 2.0) - 1.0
+    assert np.abs(np.linalg.norm(p, axis=1) - 0.6).max() < 2e-3
+    # Euler characteristic of a sphere
+    V, E, F = len(v), len(np.unique(np.sort(e, 1), axis=0)), len(f)
+    assert V - E + F == 2
+    # consistent orientation: signed volume is positive or negative for ALL faces summed, and matches 4/3 pi r^3
+    vol = np.einsum("ij,ij->i", p[f[:, 0]], np.cross(p[f[:, 1]], p[f[:, 2]])).sum() / 6.0
+    assert abs(abs(vol) - 4.0 / 3.0 * np.pi * 0.6 ** 3) < 2e-2
