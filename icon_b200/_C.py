@@ -23,6 +23,8 @@ _SIGS = {
     "icon_version": (_i, []),
     "icon_last_error": (ctypes.c_char_p, []),
     "icon_launch_count": (_i64, []),
+    "icon_profile_enable": (_i, [_i]),
+    "icon_profile_last_query": (_i, [_vp]),
     "icon_smpl_workspace_bytes": (_sz, [_i, _i]),
     "icon_smpl_prepare": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _sz, _vp]),
     "icon_query_workspace_bytes": (_sz, [_i64, _i, _i]),

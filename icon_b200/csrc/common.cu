@@ -108,7 +108,34 @@ int scan_exclusive_i32(const int32_t *in, int32_t *out, int64_t n, int64_t *d_to
     return ICON_OK;
 }
 
+static bool g_prof = false;
+static cudaEvent_t g_ev[5];
+static bool g_ev_ok = false;
+
+void profile_mark(int i, cudaStream_t stream) {
+    if (!g_prof) return;
+    if (!g_ev_ok) {
+        for (int k = 0; k < 5; ++k) cudaEventCreate(&g_ev[k]);
+        g_ev_ok = true;
+    }
+    cudaEventRecord(g_ev[i], stream);
+}
+
 }  // namespace icon
+
+extern "C" int icon_profile_enable(int on) {
+    icon::g_prof = on != 0;
+    return ICON_OK;
+}
+extern "C" int icon_profile_last_query(float *h_ms) {
+    if (!icon::g_ev_ok) {
+        icon::set_error("icon_profile_last_query: no profiled icon_query yet");
+        return ICON_EINVAL;
+    }
+    ICON_CUDA(cudaEventSynchronize(icon::g_ev[4]));
+    for (int k = 0; k < 4; ++k) ICON_CUDA(cudaEventElapsedTime(&h_ms[k], icon::g_ev[k], icon::g_ev[k + 1]));
+    return ICON_OK;
+}
 
 extern "C" int icon_version(void) { return 1; }
 extern "C" const char *icon_last_error(void) { return icon::g_err; }

@@ -65,6 +65,9 @@ struct MeshView {
 size_t mesh_ws_bytes(int V, int F);
 MeshView mesh_view(const void *ws, int V, int F);
 
+// stage timing for bench.py (icon_profile_*): mark(i) records event i on `stream` when enabled
+void profile_mark(int i, cudaStream_t stream);
+
 // exclusive scan of int32 -> int64 totals; in/out may alias.  ws: scan_ws_bytes(n).
 size_t scan_ws_bytes(int64_t n);
 int scan_exclusive_i32(const int32_t *in, int32_t *out, int64_t n, int64_t *d_total /*may be null*/,

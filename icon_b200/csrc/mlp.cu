@@ -453,7 +453,10 @@ extern "C" int icon_query(int prior, const float *points, int64_t stride_c, int6
         k_outlier_signs<<<nb, 256, 0, stream>>>(w.rec, N, sdf_clip, w.krank, w.signs);
         ICON_LAUNCHED();
         q.xyz4 = xyz4; q.rec = w.rec; q.krank = w.krank; q.signs = w.signs; q.d_K = w.d_K;
-        return launch_mlp<0>(q, stream);
+        profile_mark(3, stream);
+        rc = launch_mlp<0>(q, stream);
+        profile_mark(4, stream);
+        return rc;
     }
     int rc = run_points_only(points, stride_c, stride_n, N, h_calib, w.xyz4, stream);
     if (rc) return rc;

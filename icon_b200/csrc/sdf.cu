@@ -361,6 +361,7 @@ int run_sdf(const float *points, int64_t sc, int64_t sn, int64_t N, const float 
     Carver c(ws);
     SdfWs w = carve_sdf(c, N);
     Calib cb = make_calib(h_calib);
+    profile_mark(0, stream);
     ICON_CUDA(cudaMemsetAsync(w.count, 0, sizeof(int32_t) * (NBRICK + 1), stream));
     ICON_CUDA(cudaMemsetAsync(w.cursor, 0, sizeof(int32_t) * (NBRICK + 1), stream));
     unsigned nblk = (unsigned)((N + 255) / 256);
@@ -376,9 +377,11 @@ int run_sdf(const float *points, int64_t sc, int64_t sn, int64_t N, const float 
                                        (int)sizeof(BrickSmem)));
         attr_set = true;
     }
+    profile_mark(1, stream);
     k_sdf_brick<<<NBRICK + 1, SDF_T, sizeof(BrickSmem), stream>>>(w.xyz4, w.perm, w.count, w.offset, m,
                                                                   rec, face);
     ICON_LAUNCHED();
+    profile_mark(2, stream);
     if (xyz4_out) *xyz4_out = w.xyz4;
     return ICON_OK;
 }

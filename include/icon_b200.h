@@ -42,6 +42,13 @@ const char *icon_last_error(void);
 /* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
 int64_t icon_launch_count(void);
 
+/* Measurement hook (bench.py roofline): when enabled, icon_query records CUDA events on its
+ * stream around its stages; icon_profile_last_query synchronises on the last one and returns
+ * the stage durations of the most recent icon_query in milliseconds:
+ * h_ms[0] binning+sort, [1] SDF brick kernel, [2] outlier rank, [3] gather+MLP kernel. */
+int icon_profile_enable(int on);
+int icon_profile_last_query(float *h_ms);
+
 /* ------------------------------------------------------------------ SMPL body preparation
  * Replaces the per-call preamble of cal_sdf_batch, lib/dataset/mesh_util.py:367-372:
  * pytorch3d Meshes.verts_normals_padded (area-weighted vertex normals, deterministic

@@ -182,7 +182,7 @@ def test_query_pifu_and_pamir_vs_oracle():
 def test_query_empty_and_tiny_inputs():
     dev = _cuda()
     from icon_b200 import ops
-    pts, feat, sd, packed, body, smpl = _icon_case(dev, n=64)
+    pts, feat, sd, packed, body, smpl = _icon_case(dev, n=128)
     for n in (0, 1, 63, 65):
         out = ops.query("icon", pts[:, :n].permute(0, 2, 1).to(dev), EYE, feat.to(dev), packed, 13, body=body)
         assert out.shape == (1, 1, n)
