@@ -28,11 +28,13 @@ _SIGS = {
     "icon_smpl_workspace_bytes": (_sz, [_i, _i]),
     "icon_smpl_prepare": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _sz, _vp]),
     "icon_query_workspace_bytes": (_sz, [_i64, _i, _i]),
-    "icon_query": (_i, [_i, _vp, _i64, _i64, _i64, _vp, _vp, _i, _i, _i, _vp, _i, _vp, _i, _i, _vp, _i, _f,
+    "icon_set_mlp_impl": (_i, [_i]),
+    "icon_get_mlp_impl": (_i, []),
+    "icon_query": (_i, [_i, _vp, _i64, _i64, _i64, _vp, _vp, _i, _i, _i, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _f,
                         _vp, _vp, _sz, _vp]),
     "icon_sdf_only": (_i, [_vp, _i64, _i64, _i64, _vp, _vp, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "icon_sdf_bruteforce": (_i, [_vp, _i64, _i64, _i64, _vp, _vp, _i, _i, _vp, _vp, _vp]),
-    "icon_mlp_only": (_i, [_vp, _i, _i64, _vp, _vp, _vp]),
+    "icon_mlp_only": (_i, [_vp, _i, _i64, _vp, _vp, _vp, _vp]),
     "icon_grid_upsample": (_i, [_vp, _vp, _i, _f, _vp, _vp, _vp, _vp]),
     "icon_grid_dilate": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
     "icon_compact_workspace_bytes": (_sz, [_i]),

@@ -13,6 +13,7 @@
 // cp.async double buffering.  Algorithmic HBM traffic: 16 B xyz/in_cube + 32 B SMPL record +
 // 4 B rank in, 4 B out per point (DESIGN.md "kernels").
 #include "common.cuh"
+#include "query_common.cuh"
 
 namespace icon {
 
@@ -30,74 +31,6 @@ constexpr int OFF_B2 = OFF_W2 + 272 * 128;      // [128]
 constexpr int OFF_W3 = OFF_B2 + 128;            // [144]
 constexpr int OFF_B3 = OFF_W3 + 144;            // [1]
 static_assert(OFF_B3 + 1 == ICON_MLP_PACKED_FLOATS, "packed layout");
-
-struct QueryParams {
-    const float4 *xyz4;      // [N] transformed xyz + in_cube
-    const float *rec;        // [N][8] icon prior
-    const int32_t *krank;    // [N] exclusive outlier rank (icon)
-    const int8_t *signs;     // [K] sign of the k-th outlier (icon)
-    const int64_t *d_K;      // number of outliers (icon)
-    const float *feat;       // [C][H][W]
-    int C, H, W;
-    const float *vol;        // [7][VD][VD][VD] (pamir)
-    int VD;
-    const float *raw;        // [c0][N] (mlp_only)
-    const float *mlp;
-    int c0;
-    float clip;
-    float *out;
-    int64_t N;
-};
-
-__device__ __forceinline__ float lrelu(float x) { return x > 0.f ? x : 0.01f * x; }
-
-__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
-    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
-
-// grid_sample, bilinear, zero padding, align_corners=True; one channel plane [H][W]
-__device__ __forceinline__ float bilinear(const float *__restrict__ plane, int H, int W, float x, float y) {
-    float ix = ((x + 1.f) / 2.f) * (float)(W - 1);
-    float iy = ((y + 1.f) / 2.f) * (float)(H - 1);
-    float fx = floorf(ix), fy = floorf(iy);
-    int x0 = (int)fx, y0 = (int)fy, x1 = x0 + 1, y1 = y0 + 1;
-    float wx1 = ix - fx, wy1 = iy - fy, wx0 = (fx + 1.f) - ix, wy0 = (fy + 1.f) - iy;
-    float o = 0.f;
-    bool vx0 = x0 >= 0 && x0 < W, vx1 = x1 >= 0 && x1 < W, vy0 = y0 >= 0 && y0 < H, vy1 = y1 >= 0 && y1 < H;
-    if (vx0 && vy0) o += __ldg(plane + (size_t)y0 * W + x0) * (wx0 * wy0);
-    if (vx1 && vy0) o += __ldg(plane + (size_t)y0 * W + x1) * (wx1 * wy0);
-    if (vx0 && vy1) o += __ldg(plane + (size_t)y1 * W + x0) * (wx0 * wy1);
-    if (vx1 && vy1) o += __ldg(plane + (size_t)y1 * W + x1) * (wx1 * wy1);
-    return o;
-}
-
-// grid_sample 5-D, trilinear, zero padding, align_corners=True; one channel volume [D][D][D]
-__device__ __forceinline__ float trilinear(const float *__restrict__ v, int D, float x, float y, float z) {
-    float ix = ((x + 1.f) / 2.f) * (float)(D - 1);
-    float iy = ((y + 1.f) / 2.f) * (float)(D - 1);
-    float iz = ((z + 1.f) / 2.f) * (float)(D - 1);
-    float fx = floorf(ix), fy = floorf(iy), fz = floorf(iz);
-    int x0 = (int)fx, y0 = (int)fy, z0 = (int)fz;
-    float tx = ix - fx, ty = iy - fy, tz = iz - fz;
-    float o = 0.f;
-#pragma unroll
-    for (int dz = 0; dz < 2; ++dz)
-#pragma unroll
-        for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-            for (int dx = 0; dx < 2; ++dx) {
-                int xx = x0 + dx, yy = y0 + dy, zz = z0 + dz;
-                if (xx >= 0 && xx < D && yy >= 0 && yy < D && zz >= 0 && zz < D) {
-                    float w = (dx ? tx : 1.f - tx) * (dy ? ty : 1.f - ty) * (dz ? tz : 1.f - tz);
-                    o += __ldg(v + ((size_t)zz * D + yy) * D + xx) * w;
-                }
-            }
-    return o;
-}
 
 // MODE: 0 icon, 1 pifu, 2 pamir, 3 raw feature matrix
 template <int MODE>
@@ -371,6 +304,16 @@ static int launch_mlp(const QueryParams &q, cudaStream_t stream) {
     return ICON_OK;
 }
 
+// defined in mlp_tc.cu
+int launch_mlp_tc(int mode, const QueryParams &q, const void *blob, cudaStream_t stream);
+static int g_mlp_impl = 1;
+
+template <int MODE>
+static int launch_any(const QueryParams &q, const void *tc, cudaStream_t stream) {
+    if (g_mlp_impl == 1 && tc) return launch_mlp_tc(MODE, q, tc, stream);
+    return launch_mlp<MODE>(q, stream);
+}
+
 // defined in sdf.cu
 size_t sdf_ws_bytes(int64_t N);
 int run_sdf(const float *points, int64_t sc, int64_t sn, int64_t N, const float *h_calib, const MeshView &m,
@@ -417,12 +360,13 @@ extern "C" size_t icon_query_workspace_bytes(int64_t N, int F, int prior) {
 extern "C" int icon_query(int prior, const float *points, int64_t stride_c, int64_t stride_n, int64_t N,
                           const float *h_calib, const float *feat, int C, int H, int W,
                           const float *vol_feat, int VD, const void *mesh_ws, int V, int F,
-                          const float *mlp_packed, int c0, float sdf_clip, float *out, void *ws,
-                          size_t ws_bytes, icon_stream_t stream_) {
+                          const float *mlp_packed, const void *mlp_tc, int c0, float sdf_clip, float *out,
+                          void *ws, size_t ws_bytes, icon_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     ICON_CHECK_ARG(N >= 0 && N < (int64_t)INT32_MAX, "icon_query: N=%lld out of range", (long long)N);
     if (N == 0) return ICON_OK;
     ICON_CHECK_ARG(points && h_calib && feat && mlp_packed && out && ws, "icon_query: null pointer");
+    ICON_CHECK_ARG(((uintptr_t)mlp_tc & 15) == 0, "icon_query: mlp_tc must be 16-byte aligned");
     ICON_CHECK_ARG(c0 >= 1 && c0 <= 16, "icon_query: c0=%d unsupported (1..16)", c0);
     ICON_CHECK_ARG(H >= 2 && W >= 2, "icon_query: feature map %dx%d too small", H, W);
     {
@@ -454,7 +398,7 @@ extern "C" int icon_query(int prior, const float *points, int64_t stride_c, int6
         ICON_LAUNCHED();
         q.xyz4 = xyz4; q.rec = w.rec; q.krank = w.krank; q.signs = w.signs; q.d_K = w.d_K;
         profile_mark(3, stream);
-        rc = launch_mlp<0>(q, stream);
+        rc = launch_any<0>(q, mlp_tc, stream);
         profile_mark(4, stream);
         return rc;
     }
@@ -463,22 +407,29 @@ extern "C" int icon_query(int prior, const float *points, int64_t stride_c, int6
     q.xyz4 = w.xyz4;
     if (prior == ICON_PRIOR_PIFU) {
         ICON_CHECK_ARG(C + 1 == c0, "icon_query: pifu prior expects c0 = C + 1 (C=%d c0=%d)", C, c0);
-        return launch_mlp<1>(q, stream);
+        return launch_any<1>(q, mlp_tc, stream);
     }
     if (prior == ICON_PRIOR_PAMIR) {
         ICON_CHECK_ARG(vol_feat && VD >= 2 && C + 7 == c0, "icon_query: pamir prior expects vol_feat and c0 = C + 7");
-        return launch_mlp<2>(q, stream);
+        return launch_any<2>(q, mlp_tc, stream);
     }
     set_error("icon_query: unknown prior %d", prior);
     return ICON_EINVAL;
 }
 
-extern "C" int icon_mlp_only(const float *feature, int c0, int64_t N, const float *mlp_packed, float *out,
-                             icon_stream_t stream_) {
+extern "C" int icon_set_mlp_impl(int impl) {
+    ICON_CHECK_ARG(impl == 0 || impl == 1, "icon_set_mlp_impl: 0 (fp32) or 1 (tcgen05)");
+    g_mlp_impl = impl;
+    return ICON_OK;
+}
+extern "C" int icon_get_mlp_impl(void) { return g_mlp_impl; }
+
+extern "C" int icon_mlp_only(const float *feature, int c0, int64_t N, const float *mlp_packed, const void *mlp_tc,
+                             float *out, icon_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (N == 0) return ICON_OK;
     ICON_CHECK_ARG(feature && mlp_packed && out && c0 >= 1 && c0 <= 16, "icon_mlp_only: bad argument");
     QueryParams q{};
     q.raw = feature; q.mlp = mlp_packed; q.c0 = c0; q.out = out; q.N = N;
-    return launch_mlp<3>(q, stream);
+    return launch_any<3>(q, mlp_tc, stream);
 }

@@ -1,0 +1,472 @@
+// Fused feature gather + occupancy MLP on the 5th-generation tensor cores (tcgen05 / TMEM).
+//
+// Same contract as mlp.cu (reference: lib/net/MLP.py:49-72, lib/net/geometry.py:21-43,
+// lib/dataset/mesh_util.py:266-277, lib/net/HGPIFuNet.py:298-311, 335-363).
+//
+// Precision: every layer input x is split x = hi + lo with hi = fp16(x), lo = fp16(x - hi) (22
+// significant bits), the BN-folded weights likewise on the host, and each layer is evaluated as
+// hi*Whi + hi*Wlo + lo*Whi with fp32 accumulation in tensor memory -- three kind::f16 MMAs per
+// k-step, fp32-class accuracy (parity bar 1e-4 on the logit; measured error in DESIGN.md).
+//
+// One persistent CTA per SM, 128 query points (= 128 TMEM lanes) per tile, 320 threads:
+//   warp 0      weight producer: 1-D bulk copies (cp.async.bulk, TMA engine) of host-pre-swizzled
+//               K-major SWIZZLE_128B tiles from L2 into a 2 x 64 KB ring, mbarrier complete_tx
+//   warp 1      MMA issuer (one elected lane): tcgen05.mma.cta_group::1.kind::f16, M=128
+//   warps 2-9   workers, one TMEM lane (= query point) per thread, two threads per lane:
+//               feature gather -> x0; per 64-column chunk of layer 0: tcgen05.ld -> +bias ->
+//               LeakyReLU -> hi/lo fp16 -> tcgen05.st as the A operand (in TMEM) of layer 1; same
+//               for layer 1 -> layer 2; layer 3 (141 -> 1) as an fp32 dot product in registers.
+// Layer-0 chunks are issued two ahead of the layer-1 chunk that consumes them, so the tensor pipe
+// always has queued work while the workers convert.  TMEM map (512 columns):
+//   [0,256) layer-1 accumulator (later [0,128) layer-2 accumulator)
+//   [256,384) 2 x (hi 32 | lo 32) A-operand chunks of layer 1   } later: layer-1 activations
+//   [384,512) 2 x 64 layer-0 accumulator chunks                 } hi [256,384), lo [384,512)
+// Operand layouts were verified on hardware with tools/umma_probe.cu.
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "query_common.cuh"
+
+namespace icon {
+
+constexpr int TC_THREADS = 320;
+constexpr int TC_M = 128;
+
+// byte offsets inside the packed tensor-core weight blob (host: icon_b200/ops.py pack_mlp_tc)
+constexpr int TCB_W0 = 0;                         // hi 16384 | lo 16384, no swizzle, LBO 8192, SBO 128
+constexpr int TCB_W1 = 32768;                     // 8 x (hi 32768 | lo 32768), SW128, 256 rows x 64 k
+constexpr int TCB_W2 = TCB_W1 + 8 * 65536;        // 4 x (hi 16384 | lo 16384), SW128, 128 rows x 64 k
+constexpr int TCB_W2T = TCB_W2 + 4 * 32768;       // hi 4096 | lo 4096, no swizzle, 128 rows x 16 k
+constexpr int TCB_F32 = TCB_W2T + 8192;           // b0[512] b1[256] b2[128] w3[144] b3[1] pad
+constexpr int TCB_F32_FLOATS = 512 + 256 + 128 + 144 + 4;
+constexpr int TCB_BYTES = TCB_F32 + TCB_F32_FLOATS * 4;
+static_assert(TCB_BYTES == ICON_MLP_TC_BYTES, "blob layout");
+
+// shared memory map (bytes from a 1024-aligned base)
+constexpr int SM_STAGE = 0;                       // 2 x 65536
+constexpr int SM_W0 = 131072;                     // 32768
+constexpr int SM_X0H = SM_W0 + 32768;             // 4096  A tile of x0 (hi), no swizzle, LBO 2048, SBO 128
+constexpr int SM_X0L = SM_X0H + 4096;             // 4096
+constexpr int SM_X0F = SM_X0L + 4096;             // 2 x [16][128] fp32
+constexpr int SM_F32 = SM_X0F + 2 * 8192;         // biases etc.
+constexpr int SM_PART = SM_F32 + TCB_F32_FLOATS * 4;   // [128] fp32 layer-3 partials
+constexpr int SM_BAR = SM_PART + 512;             // 16 mbarriers
+constexpr int SM_MISC = SM_BAR + 16 * 8;
+constexpr int SM_TOTAL = SM_MISC + 64;
+constexpr int TC_SMEM_BYTES = SM_TOTAL + 1024;    // slack for manual 1024-B alignment
+
+enum { B_WFULL0 = 0, B_WFULL1, B_WEMPTY0, B_WEMPTY1, B_X0, B_ACC0F0, B_ACC0F1, B_A0F0, B_A0F1, B_A0E0, B_A0E1,
+       B_ACC1, B_ACT1, B_ACC2, B_W0RDY };
+
+// TMEM columns
+constexpr uint32_t T_ACC1 = 0, T_A0 = 256, T_ACC0 = 384, T_ACT1H = 256, T_ACT1L = 384, T_ACC2 = 0;
+
+// ---------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t s32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    uint32_t spins = 0;
+    while (true) {
+        asm volatile("{\n.reg .pred q;\nmbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\nselp.b32 %0, 1, 0, q;\n}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) break;
+        if (++spins > (1u << 27)) __trap();     // a protocol bug must fail, not hang the GPU
+    }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void mma_ss(uint32_t d, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n.reg .pred q;\nsetp.ne.b32 q, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, q;\n}" ::"r"(d),
+                 "l"(ad), "l"(bd), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a_tmem, uint64_t bd, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n.reg .pred q;\nsetp.ne.b32 q, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, q;\n}" ::"r"(d),
+                 "r"(a_tmem), "l"(bd), "r"(idesc), "r"(acc) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,"
+        "%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(addr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t addr, const uint32_t (&r)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(addr),
+                 "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+                 "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// descriptors (tools/umma_probe.cu)
+__device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr) {      // K-major, SWIZZLE_128B, SBO = 1024 B
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ uint64_t desc_nosw(uint32_t saddr, uint32_t lbo, uint32_t sbo) {   // K-major, no swizzle
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) |
+           ((uint64_t)1 << 46);
+}
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N) {     // A = B = F16, D = F32, both K-major
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// x -> (hi, lo) fp16 pairs for two values
+__device__ __forceinline__ void split2(float a, float b, uint32_t &hi, uint32_t &lo) {
+    __half2 h = __floats2half2_rn(a, b);
+    float2 hf = __half22float2(h);
+    __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+    hi = *reinterpret_cast<uint32_t *>(&h);
+    lo = *reinterpret_cast<uint32_t *>(&l);
+}
+
+// bias + LeakyReLU + split of 32 accumulator values -> 16 hi words + 16 lo words
+__device__ __forceinline__ void act_split32(const uint32_t (&acc)[32], const float *__restrict__ bias, uint32_t (&hi)[16],
+                                            uint32_t (&lo)[16]) {
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+        float4 b = *reinterpret_cast<const float4 *>(bias + i);
+        float v0 = __uint_as_float(acc[i]) + b.x, v1 = __uint_as_float(acc[i + 1]) + b.y;
+        float v2 = __uint_as_float(acc[i + 2]) + b.z, v3 = __uint_as_float(acc[i + 3]) + b.w;
+        v0 = fmaxf(v0, 0.01f * v0); v1 = fmaxf(v1, 0.01f * v1);
+        v2 = fmaxf(v2, 0.01f * v2); v3 = fmaxf(v3, 0.01f * v3);
+        split2(v0, v1, hi[i / 2], lo[i / 2]);
+        split2(v2, v3, hi[i / 2 + 1], lo[i / 2 + 1]);
+    }
+}
+
+// MODE: 0 icon, 1 pifu, 2 pamir, 3 raw feature matrix
+template <int MODE>
+__global__ void __launch_bounds__(TC_THREADS, 1) k_query_mlp_tc(QueryParams q, const uint8_t *__restrict__ blob) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = s32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t *sm = smem_raw + (base - raw);
+    float *x0f = reinterpret_cast<float *>(sm + SM_X0F);
+    const float *sf32 = reinterpret_cast<const float *>(sm + SM_F32);
+    const float *sb0 = sf32, *sb1 = sf32 + 512, *sb2 = sf32 + 768, *sw3 = sf32 + 896, *sb3 = sf32 + 1040;
+    float *spart = reinterpret_cast<float *>(sm + SM_PART);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sm + SM_MISC);
+    const uint32_t bar0 = base + SM_BAR;
+    auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t ntiles = (q.N + TC_M - 1) / TC_M;
+
+    // ------------------------------------------------------------ one-time setup
+    if (tid == 0) {
+        mbar_init(BAR(B_WFULL0), 1); mbar_init(BAR(B_WFULL1), 1);
+        mbar_init(BAR(B_WEMPTY0), 1); mbar_init(BAR(B_WEMPTY1), 1);
+        mbar_init(BAR(B_X0), 256);
+        mbar_init(BAR(B_ACC0F0), 1); mbar_init(BAR(B_ACC0F1), 1);
+        mbar_init(BAR(B_A0F0), 256); mbar_init(BAR(B_A0F1), 256);
+        mbar_init(BAR(B_A0E0), 1); mbar_init(BAR(B_A0E1), 1);
+        mbar_init(BAR(B_ACC1), 1); mbar_init(BAR(B_ACT1), 256); mbar_init(BAR(B_ACC2), 1);
+        mbar_init(BAR(B_W0RDY), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(s32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        // ======================================================== weight producer
+        if (lane == 0) {
+            // resident: W0 (hi | lo) and the fp32 tail (biases, last layer)
+            mbar_expect_tx(BAR(B_W0RDY), 32768 + TCB_F32_FLOATS * 4);
+            bulk_g2s(base + SM_W0, blob + TCB_W0, 32768, BAR(B_W0RDY));
+            bulk_g2s(base + SM_F32, blob + TCB_F32, TCB_F32_FLOATS * 4, BAR(B_W0RDY));
+            uint32_t cnt = 0;
+            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                for (int i = 0; i < 13; ++i) {
+                    const uint32_t s = cnt & 1, ph = (cnt >> 1) & 1;
+                    mbar_wait(BAR(B_WEMPTY0 + s), ph ^ 1);
+                    const uint8_t *src;
+                    uint32_t bytes;
+                    if (i < 8) { src = blob + TCB_W1 + (size_t)i * 65536; bytes = 65536; }
+                    else if (i < 12) { src = blob + TCB_W2 + (size_t)(i - 8) * 32768; bytes = 32768; }
+                    else { src = blob + TCB_W2T; bytes = 8192; }
+                    mbar_expect_tx(BAR(B_WFULL0 + s), bytes);
+                    bulk_g2s(base + SM_STAGE + s * 65536, src, bytes, BAR(B_WFULL0 + s));
+                    ++cnt;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ======================================================== MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t ID64 = idesc_f16(128, 64), ID256 = idesc_f16(128, 256), ID128 = idesc_f16(128, 128);
+            const uint64_t dx0h = desc_nosw(base + SM_X0H, 2048, 128), dx0l = desc_nosw(base + SM_X0L, 2048, 128);
+            const uint64_t dw0h = desc_nosw(base + SM_W0, 8192, 128), dw0l = desc_nosw(base + SM_W0 + 16384, 8192, 128);
+            uint32_t ph_x0 = 0, ph_a0f[2] = {0, 0}, ph_act1 = 0, cnt = 0;
+            mbar_wait(BAR(B_W0RDY), 0);
+            auto L0 = [&](int j) {
+                const uint32_t d = tmem + T_ACC0 + 64u * (uint32_t)(j & 1);
+                const uint64_t o = (uint64_t)(j * 64);              // 64 rows = 8 groups x 128 B = 1024 B -> 64 units
+                mma_ss(d, dx0h, dw0h + o, ID64, 0);
+                mma_ss(d, dx0h, dw0l + o, ID64, 1);
+                mma_ss(d, dx0l, dw0h + o, ID64, 1);
+                tc_commit(BAR(B_ACC0F0 + (j & 1)));
+            };
+            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                mbar_wait(BAR(B_X0), ph_x0); ph_x0 ^= 1;
+                tc_fence_after();
+                L0(0);
+                L0(1);
+                for (int j = 0; j < 8; ++j) {
+                    const int b = j & 1;
+                    mbar_wait(BAR(B_A0F0 + b), ph_a0f[b]); ph_a0f[b] ^= 1;
+                    const uint32_t s = cnt & 1;
+                    mbar_wait(BAR(B_WFULL0 + s), (cnt >> 1) & 1); ++cnt;
+                    tc_fence_after();
+                    const uint32_t a_hi = tmem + T_A0 + 64u * b, a_lo = a_hi + 32;
+                    const uint64_t bh = desc_sw128(base + SM_STAGE + s * 65536), bl = desc_sw128(base + SM_STAGE + s * 65536 + 32768);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        mma_ts(tmem + T_ACC1, a_hi + 8 * ks, bh + 2 * ks, ID256, (j | ks) != 0);
+                        mma_ts(tmem + T_ACC1, a_hi + 8 * ks, bl + 2 * ks, ID256, 1);
+                        mma_ts(tmem + T_ACC1, a_lo + 8 * ks, bh + 2 * ks, ID256, 1);
+                    }
+                    tc_commit(BAR(B_WEMPTY0 + s));
+                    tc_commit(BAR(B_A0E0 + b));
+                    if (j + 2 < 8) L0(j + 2);
+                }
+                tc_commit(BAR(B_ACC1));
+                // ---- layer 2
+                mbar_wait(BAR(B_ACT1), ph_act1); ph_act1 ^= 1;
+                for (int c = 0; c < 4; ++c) {
+                    const uint32_t s = cnt & 1;
+                    mbar_wait(BAR(B_WFULL0 + s), (cnt >> 1) & 1); ++cnt;
+                    tc_fence_after();
+                    const uint64_t bh = desc_sw128(base + SM_STAGE + s * 65536), bl = desc_sw128(base + SM_STAGE + s * 65536 + 16384);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const uint32_t ah = tmem + T_ACT1H + 32 * c + 8 * ks, al = tmem + T_ACT1L + 32 * c + 8 * ks;
+                        mma_ts(tmem + T_ACC2, ah, bh + 2 * ks, ID128, (c | ks) != 0);
+                        mma_ts(tmem + T_ACC2, ah, bl + 2 * ks, ID128, 1);
+                        mma_ts(tmem + T_ACC2, al, bh + 2 * ks, ID128, 1);
+                    }
+                    tc_commit(BAR(B_WEMPTY0 + s));
+                }
+                {
+                    const uint32_t s = cnt & 1;
+                    mbar_wait(BAR(B_WFULL0 + s), (cnt >> 1) & 1); ++cnt;
+                    tc_fence_after();
+                    const uint64_t th = desc_nosw(base + SM_STAGE + s * 65536, 2048, 128);
+                    const uint64_t tl = desc_nosw(base + SM_STAGE + s * 65536 + 4096, 2048, 128);
+                    mma_ss(tmem + T_ACC2, dx0h, th, ID128, 1);
+                    mma_ss(tmem + T_ACC2, dx0h, tl, ID128, 1);
+                    mma_ss(tmem + T_ACC2, dx0l, th, ID128, 1);
+                    tc_commit(BAR(B_WEMPTY0 + s));
+                }
+                tc_commit(BAR(B_ACC2));
+            }
+        }
+    } else {
+        // ======================================================== workers (8 warps, 256 threads)
+        const int q4 = warp & 3;                  // TMEM lane quarter this warp may touch
+        const int h = (warp - 2) >> 2;            // which half of the columns / features
+        const int r = q4 * 32 + lane;             // row of the tile = TMEM lane
+        const uint32_t tl = tmem + ((uint32_t)(q4 * 32) << 16);
+        const int c0 = q.c0;
+        uint32_t ph_acc0[2] = {0, 0}, ph_a0e[2] = {0, 0}, ph_acc1 = 0, ph_acc2 = 0;
+        uint32_t tcount = 0;
+        mbar_wait(BAR(B_W0RDY), 0);               // biases / last layer are in shared memory
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+            const int64_t pi = tile * TC_M + r;
+            const bool live = pi < q.N;
+            float *xf = x0f + (tcount & 1) * (16 * TC_M);
+            // ---------------- gather: 16 features of this point -> xf[j][r]
+#pragma unroll
+            for (int i = 0; i < 8; ++i) xf[(8 * h + i) * TC_M + r] = 0.f;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            float in_cube = 1.f;
+            if (MODE == 3) {
+                if (live)
+                    for (int j = h; j < c0; j += 2) xf[j * TC_M + r] = q.raw[(size_t)j * q.N + pi];
+            } else {
+                const float4 xyz = live ? q.xyz4[pi] : make_float4(0.f, 0.f, 0.f, 0.f);
+                in_cube = xyz.w;
+                if (live) {
+                    if (MODE == 0) {
+                        const int d = q.C / 2;
+                        const float4 *rp = (const float4 *)(q.rec + 8 * pi);
+                        const float4 r0 = rp[0], r1 = rp[1];
+                        const int fb = r1.w != 0.f ? 0 : d;          // feat_select: vis=1 front, vis=0 back
+                        const int lo_ch = h == 0 ? 0 : (d + 1) / 2, hi_ch = h == 0 ? (d + 1) / 2 : d;
+                        for (int ch = lo_ch; ch < hi_ch; ++ch)
+                            xf[ch * TC_M + r] = bilinear(q.feat + (size_t)(fb + ch) * q.H * q.W, q.H, q.W, xyz.x, xyz.y);
+                        if (h == 0) {
+                            float sdf = r0.x, cx = r0.y, cy = r0.z, cz = r0.w;
+                            if (fabsf(sdf) >= q.clip) {              // HGPIFuNet.py:299-304
+                                sdf = sdf > 0.f ? 1.f : -1.f;
+                                const long long K = *q.d_K, k3 = 3ll * (long long)q.krank[pi];
+                                cx = (float)q.signs[k3 % K];
+                                cy = (float)q.signs[(k3 + 1) % K];
+                                cz = (float)q.signs[(k3 + 2) % K];
+                            }
+                            xf[(d + 0) * TC_M + r] = sdf;
+                            xf[(d + 1) * TC_M + r] = cx;
+                            xf[(d + 2) * TC_M + r] = cy;
+                            xf[(d + 3) * TC_M + r] = cz;
+                        } else {
+                            xf[(d + 4) * TC_M + r] = r1.x;
+                            xf[(d + 5) * TC_M + r] = r1.y;
+                            xf[(d + 6) * TC_M + r] = r1.z;
+                        }
+                    } else if (MODE == 1) {
+                        for (int ch = h; ch < q.C; ch += 2)
+                            xf[ch * TC_M + r] = bilinear(q.feat + (size_t)ch * q.H * q.W, q.H, q.W, xyz.x, xyz.y);
+                        if (h == 0) xf[q.C * TC_M + r] = xyz.z;
+                    } else {
+                        if (h == 0) {
+                            for (int ch = 0; ch < q.C; ++ch)
+                                xf[ch * TC_M + r] = bilinear(q.feat + (size_t)ch * q.H * q.W, q.H, q.W, xyz.x, xyz.y);
+                        } else {
+                            const size_t vs = (size_t)q.VD * q.VD * q.VD;
+                            for (int ch = 0; ch < 7; ++ch)
+                                xf[(q.C + ch) * TC_M + r] = trilinear(q.vol + ch * vs, q.VD, xyz.x, xyz.y, xyz.z);
+                        }
+                    }
+                }
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            {
+                // features 8h..8h+7 of row r -> one 16-byte K-core chunk of the hi and lo A tiles
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    split2(xf[(8 * h + 2 * i) * TC_M + r], xf[(8 * h + 2 * i + 1) * TC_M + r], hi[i], lo[i]);
+                const int off = h * 2048 + (r >> 3) * 128 + (r & 7) * 16;
+                *reinterpret_cast<uint4 *>(sm + SM_X0H + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4 *>(sm + SM_X0L + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                // the previous tile's TMEM reads of this thread are complete (wait::ld); order them
+                tc_fence_before();
+                mbar_arrive(BAR(B_X0));
+            }
+            // ---------------- layer 0 chunks -> A operand of layer 1
+            for (int j = 0; j < 8; ++j) {
+                const int b = j & 1;
+                mbar_wait(BAR(B_ACC0F0 + b), ph_acc0[b]); ph_acc0[b] ^= 1;
+                tc_fence_after();
+                uint32_t acc[32], hi[16], lo[16];
+                tmem_ld32(tl + T_ACC0 + 64u * b + 32u * h, acc);
+                act_split32(acc, sb0 + 64 * j + 32 * h, hi, lo);
+                mbar_wait(BAR(B_A0E0 + b), ph_a0e[b] ^ 1); ph_a0e[b] ^= 1;
+                tc_fence_after();
+                tmem_st16(tl + T_A0 + 64u * b + 16u * h, hi);
+                tmem_st16(tl + T_A0 + 64u * b + 32u + 16u * h, lo);
+                tmem_st_wait();
+                tc_fence_before();
+                mbar_arrive(BAR(B_A0F0 + b));
+            }
+            // ---------------- layer 1 accumulator -> A operand of layer 2
+            mbar_wait(BAR(B_ACC1), ph_acc1); ph_acc1 ^= 1;
+            tc_fence_after();
+#pragma unroll 1
+            for (int t = 0; t < 4; ++t) {
+                uint32_t acc[32], hi[16], lo[16];
+                tmem_ld32(tl + T_ACC1 + 128u * h + 32u * t, acc);
+                act_split32(acc, sb1 + 128 * h + 32 * t, hi, lo);
+                tmem_st16(tl + T_ACT1H + 64u * h + 16u * t, hi);
+                tmem_st16(tl + T_ACT1L + 64u * h + 16u * t, lo);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(BAR(B_ACT1));
+            // ---------------- layer 2 accumulator -> layer 3 dot product
+            mbar_wait(BAR(B_ACC2), ph_acc2); ph_acc2 ^= 1;
+            tc_fence_after();
+            float part = 0.f;
+#pragma unroll 1
+            for (int t = 0; t < 2; ++t) {
+                uint32_t acc[32];
+                tmem_ld32(tl + T_ACC2 + 64u * h + 32u * t, acc);
+                const float *bb = sb2 + 64 * h + 32 * t, *ww = sw3 + 64 * h + 32 * t;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    float v = __uint_as_float(acc[i]) + bb[i];
+                    v = fmaxf(v, 0.01f * v);
+                    part = fmaf(ww[i], v, part);
+                }
+            }
+            if (h == 1) spart[r] = part;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (h == 0 && live) {
+                float s = part + spart[r];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) s = fmaf(sw3[128 + j], xf[j * TC_M + r], s);
+                s += sb3[0];
+                q.out[pi] = in_cube * s;
+            }
+        }
+    }
+
+    // ------------------------------------------------------------ teardown
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+    }
+}
+
+static int g_sm_count = 0;
+
+template <int MODE>
+int launch_mlp_tc_t(const QueryParams &q, const void *blob, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        ICON_CUDA(cudaFuncSetAttribute(k_query_mlp_tc<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+        attr_set = true;
+    }
+    if (!g_sm_count) {
+        int dev = 0;
+        ICON_CUDA(cudaGetDevice(&dev));
+        ICON_CUDA(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const int64_t ntiles = (q.N + TC_M - 1) / TC_M;
+    const unsigned grid = (unsigned)(ntiles < g_sm_count ? ntiles : g_sm_count);
+    k_query_mlp_tc<MODE><<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(q, (const uint8_t *)blob);
+    ICON_LAUNCHED();
+    return ICON_OK;
+}
+
+int launch_mlp_tc(int mode, const QueryParams &q, const void *blob, cudaStream_t stream) {
+    switch (mode) {
+        case 0: return launch_mlp_tc_t<0>(q, blob, stream);
+        case 1: return launch_mlp_tc_t<1>(q, blob, stream);
+        case 2: return launch_mlp_tc_t<2>(q, blob, stream);
+        default: return launch_mlp_tc_t<3>(q, blob, stream);
+    }
+}
+
+}  // namespace icon

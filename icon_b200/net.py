@@ -87,7 +87,7 @@ class MLP(nn.Module):
         """feature [1, C_in, N] -> [1, 1, N]"""
         if feature.shape[0] != 1:
             raise NotImplementedError("fused MLP kernel: B=1 (inference path)")
-        y = ops.mlp_only(feature, self.packed(), self.c0)
+        y = ops.mlp_only(feature, self.packed())
         if self.last_op is not None:
             y = self.last_op(y)
         return y
@@ -247,6 +247,8 @@ class HGPIFuNet(BasePIFuNet):
         if points.shape[0] != 1:
             raise NotImplementedError("B=1 on the inference path (seg3d_lossless.py:73, train_util.py:330)")
         regressor = regressor if regressor is not None else self.if_regressor
+        if regressor.last_op is not None:
+            raise NotImplementedError("query(): last_op (sigmoid) is the training path; test_mode=True at inference")
         if self.prior_type == "icon" and set(self.smpl_feats) != {"sdf", "cmap", "norm", "vis"}:
             raise NotImplementedError("fused query kernel implements smpl_feats = sdf, cmap, norm, vis")
         preds_list = []
@@ -259,10 +261,8 @@ class HGPIFuNet(BasePIFuNet):
                                           "(voxelisation kernel: DESIGN.md 'next')")
         with torch.no_grad():
             for im_feat in features:
-                preds = ops.query(self.prior_type, points, calibs, im_feat, regressor.packed(), regressor.c0,
+                preds = ops.query(self.prior_type, points, calibs, im_feat, regressor.packed(),
                                   body=body, vol_feat=vol, sdf_clip=self.sdf_clip)
-                if regressor.last_op is not None:
-                    preds = regressor.last_op(preds)
                 preds_list.append(preds)
         return preds_list
 

@@ -66,12 +66,22 @@ class SmplBody:
 
 
 # --------------------------------------------------------------------------- MLP packing
-def pack_mlp(sd, c0, prefix="", device=None):
-    """Fold BatchNorm1d(eval) into the 1x1 convs (lib/net/MLP.py:60-70) and pack k-major.
+MLP_TC_BYTES = 32768 + 8 * 65536 + 4 * 32768 + 8192 + (512 + 256 + 128 + 144 + 4) * 4
 
-    sd: state_dict with {prefix}filters.{l}.weight/bias and {prefix}norms.{l}.*; the kernel is
-    specialised for mlp_dim [c0,512,256,128,1], res_layers [2,3,4], norm 'batch'.
-    """
+
+class PackedMLP:
+    """BN-folded occupancy-MLP weights in the two device layouts of include/icon_b200.h:
+    `f32` (k-major fp32, FP32-FMA kernel) and `tc` (fp16 hi/lo UMMA tiles, tcgen05 kernel)."""
+
+    def __init__(self, f32, tc, c0):
+        self.f32, self.tc, self.c0 = f32, tc, c0
+
+    def to(self, device):
+        return PackedMLP(self.f32.to(device), self.tc.to(device), self.c0)
+
+
+def _fold_mlp(sd, c0, prefix=""):
+    """lib/net/MLP.py:60-70 with BatchNorm1d(eval) folded into the 1x1 convs (fp64)."""
     def g(k):
         return sd[prefix + k].detach().double().cpu()
 
@@ -96,16 +106,70 @@ def pack_mlp(sd, c0, prefix="", device=None):
             b = (b - g(f"norms.{l}.running_mean")) * s + g(f"norms.{l}.bias")
         Ws.append(W)
         bs.append(b)
-    W0t = torch.zeros(16, 512, dtype=torch.float64)
-    W0t[:c0] = Ws[0].t()
-    W2t = torch.zeros(272, 128, dtype=torch.float64)
-    W2t[:256 + c0] = Ws[2].t()
-    W3 = torch.zeros(144, dtype=torch.float64)
-    W3[:128 + c0] = Ws[3][0]
-    packed = torch.cat([W0t.reshape(-1), bs[0], Ws[1].t().contiguous().reshape(-1), bs[1], W2t.reshape(-1), bs[2],
-                        W3, bs[3]]).float()
-    assert packed.numel() == MLP_PACKED_FLOATS
-    return packed.to(device) if device is not None else packed
+    # zero-pad the c0 input columns to 16: W0 [512,16], W2 [128,272], W3 [144]
+    W0 = torch.zeros(512, 16, dtype=torch.float64); W0[:, :c0] = Ws[0]
+    W2 = torch.zeros(128, 272, dtype=torch.float64); W2[:, :256 + c0] = Ws[2]
+    W3 = torch.zeros(144, dtype=torch.float64); W3[:128 + c0] = Ws[3][0]
+    return [W0.float(), Ws[1].float(), W2.float(), W3.float()], [b.float() for b in bs]
+
+
+def _hi_lo(W):
+    import numpy as np
+    w = W.numpy().astype(np.float32)
+    hi = w.astype(np.float16)
+    lo = (w - hi.astype(np.float32)).astype(np.float16)
+    return hi, lo
+
+
+def _img_sw128(M):
+    """[rows, 64] fp16 -> K-major SWIZZLE_128B tile: 16-byte chunk index XOR (row % 8)."""
+    import numpy as np
+    rows = M.shape[0]
+    src = M.reshape(rows, 8, 8)
+    out = np.zeros_like(src)
+    r = np.arange(rows)[:, None]
+    c = np.arange(8)[None, :]
+    out[r, c ^ (r % 8)] = src[r, c]
+    return out.tobytes()
+
+
+def _img_nosw(M):
+    """[rows, 16] fp16 -> K-major no-swizzle tile [k-core][row group][8 rows][8 elems]
+    (LBO = rows/8*128 bytes, SBO = 128 bytes)."""
+    import numpy as np
+    rows, K = M.shape
+    src = M.reshape(rows // 8, 8, K // 8, 8)
+    return np.ascontiguousarray(src.transpose(2, 0, 1, 3)).tobytes()
+
+
+def pack_mlp(sd, c0, prefix="", device=None):
+    """state_dict ({prefix}filters.{l}.*, {prefix}norms.{l}.*) -> PackedMLP."""
+    import numpy as np
+    (W0, W1, W2, W3), (b0, b1, b2, b3) = _fold_mlp(sd, c0, prefix)
+    f32 = torch.cat([W0.t().contiguous().reshape(-1), b0, W1.t().contiguous().reshape(-1), b1,
+                     W2.t().contiguous().reshape(-1), b2, W3, b3]).float()
+    assert f32.numel() == MLP_PACKED_FLOATS
+    blob = bytearray()
+    h, l = _hi_lo(W0)
+    blob += _img_nosw(h) + _img_nosw(l)
+    h, l = _hi_lo(W1)
+    for j in range(8):
+        blob += _img_sw128(h[:, 64 * j:64 * j + 64]) + _img_sw128(l[:, 64 * j:64 * j + 64])
+    h, l = _hi_lo(W2)
+    for j in range(4):
+        blob += _img_sw128(h[:, 64 * j:64 * j + 64]) + _img_sw128(l[:, 64 * j:64 * j + 64])
+    blob += _img_nosw(np.ascontiguousarray(h[:, 256:272])) + _img_nosw(np.ascontiguousarray(l[:, 256:272]))
+    tail = torch.cat([b0, b1, b2, W3, b3, torch.zeros(3)]).float().numpy().tobytes()
+    blob += tail
+    assert len(blob) == MLP_TC_BYTES, (len(blob), MLP_TC_BYTES)
+    tc = torch.frombuffer(blob, dtype=torch.uint8).clone()
+    out = PackedMLP(f32, tc, c0)
+    return out.to(device) if device is not None else out
+
+
+def set_mlp_impl(name):
+    """'tcgen05' (default) or 'fp32' -- which fused gather+MLP kernel icon_query launches."""
+    check(lib.icon_set_mlp_impl({"fp32": 0, "tcgen05": 1}[name]), "icon_set_mlp_impl")
 
 
 # --------------------------------------------------------------------------- query
@@ -118,9 +182,10 @@ def _point_strides(points):
     return points, points.stride(1), points.stride(2), points.shape[2]
 
 
-def query(prior, points, calib, feat, mlp_packed, c0, body=None, vol_feat=None, sdf_clip=0.05, out=None):
+def query(prior, points, calib, feat, mlp, c0=None, body=None, vol_feat=None, sdf_clip=0.05, out=None):
     """Fused HGPIFuNet.query for one feature stack, B=1.  points [1,3,N] -> preds [1,1,N]."""
-    _need_cuda(points, feat, mlp_packed, vol_feat)
+    _need_cuda(points, feat, mlp.f32, mlp.tc, vol_feat)
+    c0 = mlp.c0
     pts, sc, sn, N = _point_strides(points)
     feat = feat.detach()
     if feat.dim() != 4 or feat.shape[0] != 1:
@@ -146,7 +211,7 @@ def query(prior, points, calib, feat, mlp_packed, c0, body=None, vol_feat=None, 
     nbytes = lib.icon_query_workspace_bytes(N, F, pid)
     ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=pts.device)
     check(lib.icon_query(pid, _p(pts), sc, sn, N, _calib_rows(calib), _p(feat), C, H, W, _p(vol_feat), VD,
-                         _p(mesh), V, F, _p(mlp_packed), c0, float(sdf_clip), _p(out), _p(ws), nbytes, _stream()),
+                         _p(mesh), V, F, _p(mlp.f32), _p(mlp.tc), c0, float(sdf_clip), _p(out), _p(ws), nbytes, _stream()),
           "icon_query")
     return out
 
@@ -168,13 +233,14 @@ def sdf_only(points, calib, body, brute=False):
     return rec, face
 
 
-def mlp_only(feature, mlp_packed, c0):
+def mlp_only(feature, mlp, c0=None):
     """MLP.forward on a [1,c0,N] feature tensor -> [1,1,N] (parity tap)."""
-    _need_cuda(feature, mlp_packed)
+    _need_cuda(feature, mlp.f32, mlp.tc)
+    c0 = mlp.c0
     f = feature.detach().float().contiguous()
     N = f.shape[2]
     out = torch.empty(1, 1, N, dtype=torch.float32, device=f.device)
-    check(lib.icon_mlp_only(_p(f), c0, N, _p(mlp_packed), _p(out), _stream()), "icon_mlp_only")
+    check(lib.icon_mlp_only(_p(f), c0, N, _p(mlp.f32), _p(mlp.tc), _p(out), _stream()), "icon_mlp_only")
     return out
 
 

@@ -71,6 +71,17 @@ int icon_smpl_prepare(const float *verts, const int64_t *faces, const float *cma
  * with k-major ("t") storage, the c0 input channels zero-padded to 16, and skip-concat
  * columns ordered [y | x0]. */
 #define ICON_MLP_PACKED_FLOATS (16 * 512 + 512 + 512 * 256 + 256 + 272 * 128 + 128 + 144 + 1)
+/* Tensor-core form of the same folded weights (host: icon_b200/ops.py pack_mlp): every matrix
+ * split W = hi + lo in fp16 and stored as ready-to-use K-major UMMA tiles (bytes):
+ *   W0  hi 16384 | lo 16384    512 rows x 16 k, no swizzle (LBO 8192, SBO 128)
+ *   W1  8 x (hi 32768 | lo 32768)   256 rows x 64 k per chunk, SWIZZLE_128B
+ *   W2  4 x (hi 16384 | lo 16384)   128 rows x 64 k per chunk, SWIZZLE_128B
+ *   W2t hi 4096 | lo 4096      128 rows x 16 k (the skip-concat x0 columns), no swizzle
+ *   f32 b0[512] b1[256] b2[128] w3[144] b3[1] pad[3] */
+#define ICON_MLP_TC_BYTES (32768 + 8 * 65536 + 4 * 32768 + 8192 + (512 + 256 + 128 + 144 + 4) * 4)
+/* 0 = FP32 FMA kernel (mlp.cu), 1 = tcgen05 fp16x3 kernel (mlp_tc.cu, default when mlp_tc != NULL) */
+int icon_set_mlp_impl(int impl);
+int icon_get_mlp_impl(void);
 
 /* ------------------------------------------------------------------ fused occupancy query
  * Replaces HGPIFuNet.query (lib/net/HGPIFuNet.py:268-367) + cal_sdf_batch
@@ -84,6 +95,7 @@ int icon_smpl_prepare(const float *verts, const int64_t *faces, const float *cma
  *   vol_feat    : pamir only: [7,D,D,D] f32; else NULL
  *   mesh_ws     : icon only: workspace filled by icon_smpl_prepare (same V,F); else NULL
  *   mlp_packed  : ICON_MLP_PACKED_FLOATS floats
+ *   mlp_tc      : ICON_MLP_TC_BYTES bytes (16-byte aligned) or NULL (-> FP32 kernel)
  *   c0          : MLP input channels (13 or 10)
  *   sdf_clip    : cfg.sdf_clip/100 (icon)
  *   out         : [N] f32 occupancy (preds[0,0,:])
@@ -93,8 +105,8 @@ size_t icon_query_workspace_bytes(int64_t N, int F, int prior);
 int icon_query(int prior, const float *points, int64_t stride_c, int64_t stride_n, int64_t N,
                const float *h_calib, const float *feat, int C, int H, int W,
                const float *vol_feat, int VD, const void *mesh_ws, int V, int F,
-               const float *mlp_packed, int c0, float sdf_clip, float *out, void *ws,
-               size_t ws_bytes, icon_stream_t stream);
+               const float *mlp_packed, const void *mlp_tc, int c0, float sdf_clip, float *out,
+               void *ws, size_t ws_bytes, icon_stream_t stream);
 
 /* Debug / parity tap: the SMPL block alone (cal_sdf_batch outputs before the outlier rule).
  * rec [N,8] f32 = sdf, cmap xyz, norm xyz, vis(0/1); face [N] i32 nearest face id. */
@@ -106,8 +118,8 @@ int icon_sdf_bruteforce(const float *points, int64_t stride_c, int64_t stride_n,
                         const float *h_calib, const void *mesh_ws, int V, int F, float *rec,
                         int32_t *face, icon_stream_t stream);
 /* MLP alone on a ready [c0,N] feature matrix (parity tap for lib/net/MLP.py:49-72). */
-int icon_mlp_only(const float *feature, int c0, int64_t N, const float *mlp_packed, float *out,
-                  icon_stream_t stream);
+int icon_mlp_only(const float *feature, int c0, int64_t N, const float *mlp_packed,
+                  const void *mlp_tc, float *out, icon_stream_t stream);
 
 /* ------------------------------------------------------------------ reconstruction engine
  * Replace the per-level body of Seg3dLossless._forward_faster

@@ -14,6 +14,17 @@ pytestmark = pytest.mark.gpu
 from icon_b200 import synthetic as S  # noqa: E402
 
 
+@pytest.fixture(params=["tcgen05", "fp32"], autouse=True)
+def mlp_impl(request):
+    """Every test runs against both fused gather+MLP kernels (mlp_tc.cu and mlp.cu)."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from icon_b200 import ops
+    ops.set_mlp_impl(request.param)
+    yield request.param
+    ops.set_mlp_impl("tcgen05")
+
+
 def _cuda():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
@@ -102,11 +113,11 @@ def test_mlp_vs_oracle_and_reference_golden(c0, golden_dir):
     packed = ops.pack_mlp(sd, c0, device=dev)
     g = np.load(os.path.join(golden_dir, "mlp_index.npz"))
     x = torch.from_numpy(g[f"mlp{c0}_x"])
-    y = ops.mlp_only(x.to(dev), packed, c0).cpu()
+    y = ops.mlp_only(x.to(dev), packed).cpu()
     assert np.abs(y.numpy() - g[f"mlp{c0}_y"]).max() <= 1e-4          # reference module's own output
     gen = torch.Generator().manual_seed(5)
     x2 = torch.randn(1, c0, 70001, generator=gen) * 1.5
-    y2 = ops.mlp_only(x2.to(dev), packed, c0).cpu()
+    y2 = ops.mlp_only(x2.to(dev), packed).cpu()
     ref = OQ.mlp_forward(sd, x2, dtype=torch.float64).float()
     err = (y2 - ref).abs()
     assert err.max() <= 1e-4, f"max {err.max().item():.3e}"
@@ -135,7 +146,7 @@ def test_query_icon_vs_oracle(c0, hw):
     from oracle import query as OQ
     pts, feat, sd, packed, body, smpl = _icon_case(dev, c0=c0, feat_hw=hw)
     samples = pts.permute(0, 2, 1)
-    out = ops.query("icon", samples.to(dev), EYE, feat.to(dev), packed, c0, body=body, sdf_clip=0.05).cpu()
+    out = ops.query("icon", samples.to(dev), EYE, feat.to(dev), packed, body=body, sdf_clip=0.05).cpu()
     ref = OQ.query(sd, [feat], samples, EYE, prior="icon", smpl=smpl, sdf_clip=0.05,
                    mlp_dtype=torch.float64)[0]
     err = (out - ref).abs()
@@ -153,7 +164,7 @@ def test_query_icon_general_calibration():
     calib[0, :3, :3] += 0.05 * torch.randn(3, 3, generator=g)
     calib[0, :3, 3] = 0.02 * torch.randn(3, generator=g)
     samples = pts.permute(0, 2, 1)
-    out = ops.query("icon", samples.to(dev), calib, feat.to(dev), packed, 13, body=body).cpu()
+    out = ops.query("icon", samples.to(dev), calib, feat.to(dev), packed, body=body).cpu()
     ref = OQ.query(sd, [feat], samples, calib, prior="icon", smpl=smpl, mlp_dtype=torch.float64)[0]
     # a general calibration moves points by ~1 ulp between baddbmm and the kernel's fma chain: allow
     # the rare point whose nearest face flips on an exact tie
@@ -169,12 +180,12 @@ def test_query_pifu_and_pamir_vs_oracle():
     packed = ops.pack_mlp(sd, 13, device=dev)
     pts = _points(30000, seed=8, spread=1.1).permute(0, 2, 1)
     feat12 = S.feature_map(12, 128, seed=1)
-    out = ops.query("pifu", pts.to(dev), EYE, feat12.to(dev), packed, 13).cpu()
+    out = ops.query("pifu", pts.to(dev), EYE, feat12.to(dev), packed).cpu()
     ref = OQ.query(sd, [feat12], pts, EYE, prior="pifu", mlp_dtype=torch.float64)[0]
     assert (out - ref).abs().max() <= 1e-4
     feat6 = S.feature_map(6, 128, seed=2)
     vol = torch.randn(1, 7, 32, 32, 32, generator=torch.Generator().manual_seed(3))
-    out = ops.query("pamir", pts.to(dev), EYE, feat6.to(dev), packed, 13, vol_feat=vol.to(dev)).cpu()
+    out = ops.query("pamir", pts.to(dev), EYE, feat6.to(dev), packed, vol_feat=vol.to(dev)).cpu()
     ref = OQ.query(sd, [feat6], pts, EYE, prior="pamir", vol_feat=vol, mlp_dtype=torch.float64)[0]
     assert (out - ref).abs().max() <= 1e-4
 
@@ -184,7 +195,7 @@ def test_query_empty_and_tiny_inputs():
     from icon_b200 import ops
     pts, feat, sd, packed, body, smpl = _icon_case(dev, n=128)
     for n in (0, 1, 63, 65):
-        out = ops.query("icon", pts[:, :n].permute(0, 2, 1).to(dev), EYE, feat.to(dev), packed, 13, body=body)
+        out = ops.query("icon", pts[:, :n].permute(0, 2, 1).to(dev), EYE, feat.to(dev), packed, body=body)
         assert out.shape == (1, 1, n)
         assert torch.isfinite(out).all()
 

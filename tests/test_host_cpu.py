@@ -40,7 +40,7 @@ def test_ops_refuse_cpu_tensors(built_lib):
     sd = S.mlp_state_dict(13, seed=1)
     packed = ops.pack_mlp(sd, 13)
     with pytest.raises(_C.IconError):
-        ops.mlp_only(torch.zeros(1, 13, 8), packed, 13)      # no CPU fallback
+        ops.mlp_only(torch.zeros(1, 13, 8), packed)      # no CPU fallback
 
 
 @pytest.mark.parametrize("c0", [13, 10])
@@ -49,7 +49,9 @@ def test_pack_mlp_folding_matches_oracle(built_lib, c0):
     from icon_b200 import ops
     from oracle import query as OQ
     sd = S.mlp_state_dict(c0, seed=4)
-    p = ops.pack_mlp(sd, c0).double()
+    pk = ops.pack_mlp(sd, c0)
+    assert pk.tc.numel() == ops.MLP_TC_BYTES and pk.tc.dtype == torch.uint8
+    p = pk.f32.double()
     o = 0
 
     def take(n):
