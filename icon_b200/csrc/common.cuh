@@ -54,13 +54,38 @@ struct Carver {
 };
 
 // ---------------------------------------------------------------- mesh workspace layout
+constexpr int BVH_MAX_LEVELS = 10;   // 4-ary implicit tree over leaves of 4 Morton-sorted faces
+constexpr int RAY_GRID = 256;        // yz cell grid for the +x ray parity
+constexpr int RAY_LIST_PER_FACE = 64;
+
+struct MeshHeader {                  // device-resident, written by icon_smpl_prepare
+    float y0, z0, inv_cy, inv_cz;    // ray grid origin / inverse cell size over the mesh yz box
+    int ray_overflow;                // 1 -> cell lists overflowed: kernels fall back to all faces
+    int pad[3];
+};
+
 struct MeshView {
-    const float4 *tri;    // [F][3]: (a.xyz, ab.x) (ab.yz, ac.xy) (ac.z, -, -, -)
+    const float4 *tri;    // [F][3]: (a.xyz, ab.x) (ab.yz, ac.xy) (ac.z, -, -, -), original face order
     const float4 *sph;    // [F]: bounding sphere (centre xyz, radius), conservative
     const float4 *attr;   // [F][6]: normals 9, cmap 9, vis 3, pad 3
-    const float4 *rbox;   // [F][2]: (ymin, ymax, zmin, zmax) (xmax, -, -, -)
+    const float4 *rbox;   // [F][2]: (ymin, ymax, zmin, zmax) (xmax, xmin, -, -)
     float *vnormals;      // [V][3] scratch
+    // Morton-sorted copy + implicit AABB tree
+    unsigned long long *keys;   // [F] morton << 32 | face
+    int32_t *order;       // [F] sorted position -> face id
+    float4 *tri_s;        // [F][3] sorted
+    float4 *sph_s;        // [F] sorted
+    float4 *nodes;        // [total_nodes][2]: (min.xyz, -) (max.xyz, -), level 0 (leaves) first
+    // ray grid
+    int32_t *rcount;      // [RAY_GRID^2 + 1]
+    int32_t *roff;        // [RAY_GRID^2 + 1]
+    int32_t *rlist;       // [F * RAY_LIST_PER_FACE]
+    MeshHeader *hdr;
+    void *scan_ws;
     int V, F;
+    int nlevels;
+    int lvl_cnt[BVH_MAX_LEVELS];
+    int lvl_off[BVH_MAX_LEVELS];
 };
 size_t mesh_ws_bytes(int V, int F);
 MeshView mesh_view(const void *ws, int V, int F);

@@ -1,34 +1,27 @@
-// SMPL-body SDF block of the occupancy query, brick-culled.  Compiled with -fmad=false.
+// SMPL-body SDF block of the occupancy query.  Compiled with -fmad=false.
 //
 // Replaces, per query point (reference: cal_sdf_batch, lib/dataset/mesh_util.py:357-396):
 //   kaolin point_to_mesh_distance  -> nearest face (lowest index on ties) + squared distance
 //   kaolin check_sign              -> +x ray parity
 //   barycentric_coordinates_of_projection + the four gathers -> cmap / normal / vis
 //
-// Design (DESIGN.md "SDF bricks"): the cube [-1,1]^3 is cut into 32^3 bricks of edge 1/16.
-// Points are counting-sorted by brick; one CTA owns one non-empty brick and
-//   phase 1  culls the F faces against the brick centre c: with d_c = min_f d(c,f) and brick
-//            radius r, only faces with d(c,f) <= d_c + 2r can be nearest to ANY point of the
-//            brick (triangle inequality) -> candidate list in shared memory; a second list
-//            keeps the faces whose yz-box meets the brick's (+x ray candidates);
-//   phase 2  every thread takes a point and scans the candidate list with a bounding-sphere
-//            reject in front of the exact point-triangle distance, then the ray list.
-// Results are identical to the brute-force scan over all faces (icon_sdf_bruteforce and the CPU
-// oracle): culling is conservative and the per-face arithmetic is the same code (geom.cuh).
+// Design (DESIGN.md "SDF"): one thread per query point.
+//   nearest face  depth-first walk of the implicit 4-ary AABB tree over Morton-sorted faces
+//                 (icon_smpl_prepare), children visited near-to-far, a subtree is skipped only
+//                 when its box is strictly farther than the current best (with float slack), a
+//                 face only when its bounding sphere is; ties resolve to the lowest ORIGINAL
+//                 face index, exactly like the brute-force scan.
+//   sign          the faces listed in the point's yz cell (256 x 256 grid over the mesh's yz
+//                 box) are the only ones a +x ray can hit; each is tested with the same
+//                 Moller-Trumbore code as the brute-force scan, so the hit COUNT is identical.
+// Results are identical to brute force over all faces (icon_sdf_bruteforce, the CPU oracle):
+// the pruning is conservative and the per-face arithmetic is the same code (geom.cuh).
 #include <float.h>
 
 #include "common.cuh"
 #include "geom.cuh"
 
 namespace icon {
-
-constexpr int NB = 32;                 // bricks per axis
-constexpr int NBRICK = NB * NB * NB;   // + 1 overflow brick for points outside [-1,1]^3
-constexpr float BRICK_H = 2.0f / NB;
-constexpr int SDF_T = 256;
-constexpr int CAND1_MAX = 6144;        // faces surviving the sphere cull (with exact distance)
-constexpr int CAND_MAX = 6144;         // final nearest-face candidates
-constexpr int RCAND_MAX = 3072;        // +x ray candidates
 
 struct Calib {
     float r[9];
@@ -43,58 +36,6 @@ __device__ __forceinline__ V3 load_point(const float *__restrict__ pts, int64_t 
     o.y = fmaf(cb.r[5], pz, fmaf(cb.r[4], py, cb.r[3] * px)) + cb.t[1];
     o.z = fmaf(cb.r[8], pz, fmaf(cb.r[7], py, cb.r[6] * px)) + cb.t[2];
     return o;
-}
-
-__device__ __forceinline__ int brick_of(V3 p) {
-    bool inside = p.x >= -1.f && p.x <= 1.f && p.y >= -1.f && p.y <= 1.f && p.z >= -1.f && p.z <= 1.f;
-    if (!inside) return NBRICK;
-    int bx = min(NB - 1, (int)((p.x + 1.f) * (NB * 0.5f)));
-    int by = min(NB - 1, (int)((p.y + 1.f) * (NB * 0.5f)));
-    int bz = min(NB - 1, (int)((p.z + 1.f) * (NB * 0.5f)));
-    return (bz * NB + by) * NB + bx;
-}
-
-// xyz4[i] = (x, y, z, in_cube); bid[i]; count[brick]++ (warp-aggregated)
-__global__ void k_points_bin(const float *__restrict__ pts, int64_t sc, int64_t sn, int64_t N,
-                             Calib cb, float4 *__restrict__ xyz4, uint16_t *__restrict__ bid,
-                             int32_t *__restrict__ count) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool live = i < N;
-    int b = -1;
-    if (live) {
-        V3 p = load_point(pts, sc, sn, i, cb);
-        // HGPIFuNet.py:270-275: in_cube = all(-1 < xyz < 1), strict
-        float in_cube = (p.x > -1.f && p.x < 1.f && p.y > -1.f && p.y < 1.f && p.z > -1.f && p.z < 1.f)
-                            ? 1.f : 0.f;
-        xyz4[i] = make_float4(p.x, p.y, p.z, in_cube);
-        b = brick_of(p);
-        bid[i] = (uint16_t)b;
-    }
-    unsigned act = __ballot_sync(0xffffffffu, live);
-    if (live) {
-        unsigned peers = __match_any_sync(act, b);
-        int leader = __ffs(peers) - 1;
-        if ((threadIdx.x & 31) == leader) atomicAdd(&count[b], __popc(peers));
-    }
-}
-
-__global__ void k_points_scatter(const uint16_t *__restrict__ bid, int64_t N,
-                                 const int32_t *__restrict__ offset, int32_t *__restrict__ cursor,
-                                 int32_t *__restrict__ perm) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool live = i < N;
-    int b = live ? (int)bid[i] : -1;
-    unsigned act = __ballot_sync(0xffffffffu, live);
-    if (live) {
-        unsigned peers = __match_any_sync(act, b);
-        int lane = threadIdx.x & 31;
-        int leader = __ffs(peers) - 1;
-        int base = 0;
-        if (lane == leader) base = atomicAdd(&cursor[b], __popc(peers));
-        base = __shfl_sync(peers, base, leader);
-        int rank = __popc(peers & ((1u << lane) - 1u));
-        perm[offset[b] + base + rank] = (int32_t)i;
-    }
 }
 
 // cmap / normal / vis of the winning face + final sdf; mirrors the tail of oracle_cal_sdf().
@@ -133,160 +74,249 @@ __device__ __forceinline__ void emit_record(V3 p, int bi, float best, int hits, 
     if (face) face[idx] = bi;
 }
 
-struct BrickSmem {
-    int c1_f[CAND1_MAX];
-    float c1_d[CAND1_MAX];
-    int cand[CAND_MAX];
-    int rcand[RCAND_MAX];
-    float red_f[SDF_T / 32];
-    int red_i[SDF_T / 32];
-    int n1, ncand, nrc, all_mode, ray_all, f0;
-    float ub, dmin;
+constexpr int SW_T = 128;               // 4 warps per block, one warp = 32 Morton-adjacent points
+constexpr int NBIN_AX = 128;            // Morton bins per axis over [-1,1]^3 (+1 overflow bin)
+constexpr int NBIN = NBIN_AX * NBIN_AX * NBIN_AX;
+constexpr int FR_CAP = 2048;            // frontier / leaf list capacity per warp
+
+__device__ __forceinline__ float box_dist2(V3 p, float4 lo, float4 hi) {
+    float dx = fmaxf(fmaxf(lo.x - p.x, p.x - hi.x), 0.f);
+    float dy = fmaxf(fmaxf(lo.y - p.y, p.y - hi.y), 0.f);
+    float dz = fmaxf(fmaxf(lo.z - p.z, p.z - hi.z), 0.f);
+    return fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+}
+
+__device__ __forceinline__ unsigned spread7(unsigned v) {      // <= 10 bits -> every third bit
+    v = (v | (v << 16)) & 0x030000FFu;
+    v = (v | (v << 8)) & 0x0300F00Fu;
+    v = (v | (v << 4)) & 0x030C30C3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+
+__device__ __forceinline__ int bin_of(V3 p) {
+    const bool inside = p.x >= -1.f && p.x <= 1.f && p.y >= -1.f && p.y <= 1.f && p.z >= -1.f && p.z <= 1.f;
+    if (!inside) return NBIN;
+    const unsigned bx = min(NBIN_AX - 1, (int)((p.x + 1.f) * (NBIN_AX * 0.5f)));
+    const unsigned by = min(NBIN_AX - 1, (int)((p.y + 1.f) * (NBIN_AX * 0.5f)));
+    const unsigned bz = min(NBIN_AX - 1, (int)((p.z + 1.f) * (NBIN_AX * 0.5f)));
+    return (int)(spread7(bx) | (spread7(by) << 1) | (spread7(bz) << 2));
+}
+
+// xyz4[i] = (x, y, z, in_cube); bid[i] = Morton bin; count[bin]++ (warp-aggregated atomics)
+__global__ void k_points_bin(const float *__restrict__ pts, int64_t sc, int64_t sn, int64_t N, Calib cb,
+                             float4 *__restrict__ xyz4, int32_t *__restrict__ bid, int32_t *__restrict__ count) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < N;
+    int b = -1;
+    if (live) {
+        const V3 p = load_point(pts, sc, sn, i, cb);
+        // HGPIFuNet.py:270-275: in_cube = all(-1 < xyz < 1), strict
+        const float in_cube = (p.x > -1.f && p.x < 1.f && p.y > -1.f && p.y < 1.f && p.z > -1.f && p.z < 1.f) ? 1.f : 0.f;
+        xyz4[i] = make_float4(p.x, p.y, p.z, in_cube);
+        b = bin_of(p);
+        bid[i] = b;
+    }
+    const unsigned act = __ballot_sync(0xffffffffu, live);
+    if (live) {
+        const unsigned peers = __match_any_sync(act, b);
+        if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&count[b], __popc(peers));
+    }
+}
+
+__global__ void k_points_scatter(const int32_t *__restrict__ bid, int64_t N, const int32_t *__restrict__ offset,
+                                 int32_t *__restrict__ cursor, int32_t *__restrict__ perm) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < N;
+    const int b = live ? bid[i] : -1;
+    const unsigned act = __ballot_sync(0xffffffffu, live);
+    if (live) {
+        const unsigned peers = __match_any_sync(act, b);
+        const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(&cursor[b], __popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        perm[offset[b] + base + __popc(peers & ((1u << lane) - 1u))] = (int32_t)i;
+    }
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+    for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+    for (int o = 16; o; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+#ifdef ICON_SDF_STATS
+__device__ unsigned long long g_stats[8];   // warps, overflow warps, sum leaves, sum faces, sum exact tests, sum ray tests
+#define STAT(i, v) do { if (lane == 0) atomicAdd(&g_stats[i], (unsigned long long)(v)); } while (0)
+#else
+#define STAT(i, v) do { } while (0)
+#endif
+
+struct WarpSmem {
+    unsigned short fr[2][FR_CAP];      // node / leaf ids (leaf count <= 65535 is checked by the host)
 };
 
-__global__ void __launch_bounds__(SDF_T) k_sdf_brick(const float4 *__restrict__ xyz4,
-                                                     const int32_t *__restrict__ perm,
-                                                     const int32_t *__restrict__ count,
-                                                     const int32_t *__restrict__ offset, MeshView m,
-                                                     float *__restrict__ rec, int32_t *__restrict__ face) {
+__device__ __forceinline__ float box_far2(V3 p, float4 lo, float4 hi) {   // squared distance to the farthest corner
+    float dx = fmaxf(fabsf(lo.x - p.x), fabsf(hi.x - p.x));
+    float dy = fmaxf(fabsf(lo.y - p.y), fabsf(hi.y - p.y));
+    float dz = fmaxf(fabsf(lo.z - p.z), fabsf(hi.z - p.z));
+    return fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+}
+
+__global__ void __launch_bounds__(SW_T) k_sdf_warp(const float4 *__restrict__ xyz4, const int32_t *__restrict__ perm,
+                                                   int64_t N, MeshView m, float *__restrict__ rec,
+                                                   int32_t *__restrict__ face) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    BrickSmem &S = *reinterpret_cast<BrickSmem *>(smem_raw);
-    const int b = blockIdx.x;
-    const int cnt = count[b];
-    if (cnt == 0) return;
-    const int off = offset[b];
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int F = m.F;
-    const bool overflow = (b == NBRICK);
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    WarpSmem &S = reinterpret_cast<WarpSmem *>(smem_raw)[wib];
+    const int64_t pos = ((int64_t)blockIdx.x * (SW_T / 32) + wib) * 32 + lane;
+    const int64_t pos0 = pos - lane;
+    if (pos0 >= N) return;                                   // whole warp out of range
+    const bool live = pos < N;
+    const int64_t idx = perm[live ? pos : pos0];
+    const float4 q = xyz4[idx];
+    const V3 p = mk3(q.x, q.y, q.z);
+    // warp bounding sphere (box centre, max distance)
+    const V3 c = mk3(0.5f * (warp_min(p.x) + warp_max(p.x)), 0.5f * (warp_min(p.y) + warp_max(p.y)),
+                     0.5f * (warp_min(p.z) + warp_max(p.z)));
+    const float rw = warp_max(sqrtf(dot3(sub3(p, c), sub3(p, c)))) * 1.00001f + 1e-6f;
 
-    if (tid == 0) {
-        S.n1 = 0; S.ncand = 0; S.nrc = 0;
-        S.all_mode = overflow ? 1 : 0;
-        S.ray_all = overflow ? 1 : 0;
-        S.f0 = 0x7fffffff;
+    float best = FLT_MAX;
+    int bi = 0x7fffffff;
+    auto try_face = [&](int k) {                             // exact test of sorted face k for this lane
+        const Tri tr = load_tri(m.tri_s + 3 * (size_t)k);
+        const float d = tri_sqdist(p, tr.a, tr.ab, tr.ac);
+        const int f = __ldg(m.order + k);
+        if (d < best || (d == best && f < bi)) { best = d; bi = f; }
+    };
+
+    // ---- phase A: greedy descent towards the warp centre -> a first bound for every lane
+    {
+        int node = 0;
+        for (int lvl = m.nlevels - 1; lvl > 0; --lvl) {
+            const int ch = 4 * node + (lane & 3);
+            float a = FLT_MAX;
+            int ai = ch;
+            if (ch < m.lvl_cnt[lvl - 1]) {
+                const float4 *nb = m.nodes + 2 * ((size_t)m.lvl_off[lvl - 1] + ch);
+                a = box_dist2(c, __ldg(nb), __ldg(nb + 1));
+            }
+            for (int o = 1; o <= 2; o <<= 1) {               // min over the 4 children (lanes 4j..4j+3)
+                const float ob = __shfl_xor_sync(0xffffffffu, a, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, ai, o);
+                if (ob < a || (ob == a && oi < ai)) { a = ob; ai = oi; }
+            }
+            node = __shfl_sync(0xffffffffu, ai, 0);
+        }
+        for (int k = 4 * node; k < min(4 * node + 4, m.F); ++k) try_face(k);
     }
-    __syncthreads();
+    const float ubw = warp_max(sqrtf(best));                  // every lane's nearest is within ubw
+    float lim = (ubw + rw) * 1.00001f + 1e-6f;                // bound on d(warp centre, any lane's nearest face)
+    float lim2 = lim * lim;
 
-    if (!overflow) {
-        const int bx = b % NB, by = (b / NB) % NB, bz = b / (NB * NB);
-        const V3 c = mk3(-1.f + (bx + 0.5f) * BRICK_H, -1.f + (by + 0.5f) * BRICK_H,
-                         -1.f + (bz + 0.5f) * BRICK_H);
-        const float hr = 0.5f * BRICK_H + 1e-5f;                 // half edge, with binning slack
-        const float r2 = 2.0f * (hr * 1.7320509f) + 1e-5f;       // 2 * brick radius
-
-        // ---- pass A: upper bound on d_c from the bounding spheres
-        float ub = FLT_MAX;
-        for (int f = tid; f < F; f += SDF_T) {
-            float4 s = __ldg(m.sph + f);
-            float dx = c.x - s.x, dy = c.y - s.y, dz = c.z - s.z;
-            float d = sqrtf(dx * dx + dy * dy + dz * dz) + s.w;
-            ub = fminf(ub, d);
-        }
-        for (int o = 16; o; o >>= 1) ub = fminf(ub, __shfl_xor_sync(0xffffffffu, ub, o));
-        if (lane == 0) S.red_f[wid] = ub;
-        __syncthreads();
-        if (tid == 0) {
-            float u = S.red_f[0];
-            for (int w = 1; w < SDF_T / 32; ++w) u = fminf(u, S.red_f[w]);
-            S.ub = u;
-        }
-        __syncthreads();
-        const float lim1 = S.ub * 1.00001f + r2 + 1e-5f;
-
-        // ---- pass B: exact centre distance for faces whose sphere lower bound passes;
-        //      in the same sweep collect +x-ray candidates by yz box
-        const float ylo = c.y - hr - 1e-4f, yhi = c.y + hr + 1e-4f;
-        const float zlo = c.z - hr - 1e-4f, zhi = c.z + hr + 1e-4f;
-        const float xlo = c.x - hr - 1e-4f;
-        float dmin = FLT_MAX;
-        int fmin = 0x7fffffff;
-        for (int f = tid; f < F; f += SDF_T) {
-            float4 s = __ldg(m.sph + f);
-            float dx = c.x - s.x, dy = c.y - s.y, dz = c.z - s.z;
-            float lb = sqrtf(dx * dx + dy * dy + dz * dz) - s.w;
-            if (lb <= lim1) {
-                Tri t = load_tri(m.tri + 3 * (size_t)f);
-                float d2 = tri_sqdist(c, t.a, t.ab, t.ac);
-                int slot = atomicAdd(&S.n1, 1);
-                if (slot < CAND1_MAX) { S.c1_f[slot] = f; S.c1_d[slot] = d2; }
-                if (d2 < dmin || (d2 == dmin && f < fmin)) { dmin = d2; fmin = f; }
-            }
-            float4 rb = __ldg(m.rbox + 2 * (size_t)f);
-            float xmax = __ldg(&m.rbox[2 * (size_t)f + 1].x);
-            if (rb.x <= yhi && rb.y >= ylo && rb.z <= zhi && rb.w >= zlo && xmax >= xlo) {
-                int slot = atomicAdd(&S.nrc, 1);
-                if (slot < RCAND_MAX) S.rcand[slot] = f;
-            }
-        }
-        for (int o = 16; o; o >>= 1) {
-            float od = __shfl_xor_sync(0xffffffffu, dmin, o);
-            int of = __shfl_xor_sync(0xffffffffu, fmin, o);
-            if (od < dmin || (od == dmin && of < fmin)) { dmin = od; fmin = of; }
-        }
-        if (lane == 0) { S.red_f[wid] = dmin; S.red_i[wid] = fmin; }
-        __syncthreads();
-        if (tid == 0) {
-            float d = S.red_f[0]; int f = S.red_i[0];
-            for (int w = 1; w < SDF_T / 32; ++w)
-                if (S.red_f[w] < d || (S.red_f[w] == d && S.red_i[w] < f)) { d = S.red_f[w]; f = S.red_i[w]; }
-            S.dmin = d; S.f0 = f;
-            if (S.n1 > CAND1_MAX) S.all_mode = 1;
-            if (S.nrc > RCAND_MAX) S.ray_all = 1;
-        }
-        __syncthreads();
-
-        // ---- pass C: keep faces with d(c,f) <= d_c + 2r
-        if (!S.all_mode) {
-            float lim = sqrtf(S.dmin) * 1.00001f + r2 + 1e-5f;
-            float lim2 = lim * lim;
-            int n1 = S.n1;
-            for (int k = tid; k < n1; k += SDF_T) {
-                if (S.c1_d[k] <= lim2) {
-                    int slot = atomicAdd(&S.ncand, 1);
-                    S.cand[slot] = S.c1_f[k];     // ncand <= n1 <= CAND1_MAX == CAND_MAX
+    // ---- phase B: breadth-first cull of the tree, 32 child boxes per step.  The bound also
+    //      tightens on the way down: some face lies within the nearest far-corner distance of c,
+    //      so every lane's nearest face is within that + 2 rw of c.
+    int cur = 0, n = 1;
+    bool overflow = false;
+    if (lane == 0) S.fr[0][0] = 0;
+    __syncwarp();
+    for (int lvl = m.nlevels - 1; lvl > 0 && !overflow; --lvl) {
+        int nn = 0;
+        float far2 = FLT_MAX;
+        const int ccnt = m.lvl_cnt[lvl - 1];
+        const float4 *nodes = m.nodes + 2 * (size_t)m.lvl_off[lvl - 1];
+        for (int base = 0; base < n; base += 8) {
+            const int slot = base + (lane >> 2);
+            bool pass = false;
+            int ch = 0;
+            if (slot < n) {
+                ch = 4 * (int)S.fr[cur][slot] + (lane & 3);
+                if (ch < ccnt) {
+                    const float4 lo = __ldg(nodes + 2 * (size_t)ch), hi = __ldg(nodes + 2 * (size_t)ch + 1);
+                    pass = box_dist2(c, lo, hi) <= lim2;
+                    far2 = fminf(far2, box_far2(c, lo, hi));
                 }
             }
+            const unsigned mask = __ballot_sync(0xffffffffu, pass);
+            const int at = nn + __popc(mask & ((1u << lane) - 1u));
+            if (pass && at < FR_CAP) S.fr[cur ^ 1][at] = (unsigned short)ch;
+            nn += __popc(mask);
         }
-        __syncthreads();
+        if (nn > FR_CAP) overflow = true;
+        n = nn;
+        cur ^= 1;
+        const float l2 = (sqrtf(warp_min(far2)) + 2.f * rw) * 1.00001f + 1e-6f;
+        if (l2 < lim) { lim = l2; lim2 = l2 * l2; }
+        __syncwarp();
     }
-
-    const bool all_mode = S.all_mode != 0, ray_all = S.ray_all != 0;
-    const int ncand = all_mode ? F : S.ncand;
-    const int nrc = ray_all ? F : S.nrc;
-    const int f0 = S.f0;
-
-    // ---- phase 2: one point per thread
-    for (int i = tid; i < cnt; i += SDF_T) {
-        const int64_t idx = perm[off + i];
-        float4 q = xyz4[idx];
-        V3 p = mk3(q.x, q.y, q.z);
-        float best = FLT_MAX;
-        int bi = 0x7fffffff;
-        if (!all_mode) {
-            Tri t = load_tri(m.tri + 3 * (size_t)f0);
-            best = tri_sqdist(p, t.a, t.ab, t.ac);
-            bi = f0;
-        }
+    STAT(0, 1); STAT(1, overflow ? 1 : 0); STAT(2, n);
+    // ---- phases C+D: 32 faces (8 leaves) at a time: cull by bounding sphere against the warp bound,
+    //      then every lane tests the survivors against its own best
+    {
         float sb = sqrtf(best);
-        for (int k = 0; k < ncand; ++k) {
-            int f = all_mode ? k : S.cand[k];
-            float4 s = __ldg(m.sph + f);
-            float dx = p.x - s.x, dy = p.y - s.y, dz = p.z - s.z;
-            float dd = dx * dx + dy * dy + dz * dz;
-            float lim = sb + s.w + 1e-6f;
-            if (dd > lim * lim * 1.00001f) continue;     // sphere lower bound beats current best
-            Tri t = load_tri(m.tri + 3 * (size_t)f);
-            float d = tri_sqdist(p, t.a, t.ab, t.ac);
-            if (d < best || (d == best && f < bi)) { best = d; bi = f; sb = sqrtf(d); }
+        auto lane_test = [&](int k) {
+            const float4 s = __ldg(m.sph_s + k);
+            const float dx = p.x - s.x, dy = p.y - s.y, dz = p.z - s.z;
+            const float dd = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+            const float l = sb + s.w + 1e-6f;
+            if (dd > l * l * 1.00001f) return;                 // sphere lower bound beats this lane's best
+            const float before = best;
+            try_face(k);
+            if (best != before) sb = sqrtf(best);
+        };
+        if (!overflow) {
+            for (int base = 0; base < n; base += 8) {
+                const int slot = base + (lane >> 2);
+                bool pass = false;
+                int k = 0;
+                if (slot < n) {
+                    k = 4 * (int)S.fr[cur][slot] + (lane & 3);
+                    if (k < m.F) {
+                        const float4 s = __ldg(m.sph_s + k);
+                        const float dx = c.x - s.x, dy = c.y - s.y, dz = c.z - s.z;
+                        const float l2 = lim + s.w;
+                        pass = fmaf(dz, dz, fmaf(dy, dy, dx * dx)) <= l2 * l2;
+                    }
+                }
+                unsigned mask = __ballot_sync(0xffffffffu, pass);
+                STAT(3, __popc(mask));
+                while (mask) {
+                    const int src = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    lane_test(__shfl_sync(0xffffffffu, k, src));
+                }
+            }
+        } else {
+            for (int k = 0; k < m.F; ++k) lane_test(k);
         }
-        int hits = 0;
-        for (int k = 0; k < nrc; ++k) {
-            int f = ray_all ? k : S.rcand[k];
-            Tri t = load_tri(m.tri + 3 * (size_t)f);
-            hits += ray_hit_px(p, t.a, t.ab, t.ac);
-        }
-        emit_record(p, bi, best, hits, m, rec, face, idx);
     }
+    // ---- +x ray parity
+    int hits = 0;
+    const MeshHeader h = *m.hdr;
+    if (!h.ray_overflow) {
+        const float fy = (p.y - h.y0) * h.inv_cy, fz = (p.z - h.z0) * h.inv_cz;
+        if (fy >= 0.f && fy < (float)RAY_GRID && fz >= 0.f && fz < (float)RAY_GRID) {
+            const int cc = (int)fz * RAY_GRID + (int)fy;
+            const int k0 = __ldg(m.roff + cc), k1 = __ldg(m.roff + cc + 1);
+            for (int k = k0; k < k1; ++k) {
+                const int f = __ldg(m.rlist + k);
+                if (__ldg(&m.rbox[2 * (size_t)f + 1].x) < p.x - 1e-3f) continue;     // wholly behind the ray origin
+                const Tri tr = load_tri(m.tri + 3 * (size_t)f);
+                hits += ray_hit_px(p, tr.a, tr.ab, tr.ac);
+            }
+        }
+    } else {
+        for (int f = 0; f < m.F; ++f) {
+            const Tri tr = load_tri(m.tri + 3 * (size_t)f);
+            hits += ray_hit_px(p, tr.a, tr.ab, tr.ac);
+        }
+    }
+    if (live) emit_record(p, bi, best, hits, m, rec, face, idx);
 }
 
 // brute force: every point against every face, faces staged through shared memory
@@ -321,24 +351,19 @@ __global__ void __launch_bounds__(256) k_sdf_brute(const float *__restrict__ pts
 // ---------------------------------------------------------------- host-side pipeline pieces
 struct SdfWs {
     float4 *xyz4;
-    uint16_t *bid;
-    int32_t *perm;
-    int32_t *count, *offset, *cursor;
+    int32_t *bid, *perm, *count, *offset;
     void *scan_ws;
 };
-
 static SdfWs carve_sdf(Carver &c, int64_t N) {
     SdfWs w;
     w.xyz4 = c.take<float4>((size_t)N);
-    w.bid = c.take<uint16_t>((size_t)N);
+    w.bid = c.take<int32_t>((size_t)N);
     w.perm = c.take<int32_t>((size_t)N);
-    w.count = c.take<int32_t>(NBRICK + 1);
-    w.offset = c.take<int32_t>(NBRICK + 1);
-    w.cursor = c.take<int32_t>(NBRICK + 1);
-    w.scan_ws = c.take<char>(scan_ws_bytes(NBRICK + 1));
+    w.count = c.take<int32_t>(NBIN + 1);
+    w.offset = c.take<int32_t>(NBIN + 1);
+    w.scan_ws = c.take<char>(scan_ws_bytes(NBIN + 1));
     return w;
 }
-
 size_t sdf_ws_bytes(int64_t N) {
     Carver c(nullptr);
     carve_sdf(c, N);
@@ -354,7 +379,8 @@ Calib make_calib(const float *h) {
     return cb;
 }
 
-// Runs binning + brick kernel.  Leaves xyz4 (with in_cube in .w) in the workspace for the MLP stage.
+// orthogonal() + in_cube, Morton binning, warp-cooperative SDF.  Leaves xyz4 (in_cube in .w) in the
+// workspace for the MLP stage.
 int run_sdf(const float *points, int64_t sc, int64_t sn, int64_t N, const float *h_calib,
             const MeshView &m, float *rec, int32_t *face, void *ws, float4 **xyz4_out,
             cudaStream_t stream) {
@@ -362,24 +388,23 @@ int run_sdf(const float *points, int64_t sc, int64_t sn, int64_t N, const float 
     SdfWs w = carve_sdf(c, N);
     Calib cb = make_calib(h_calib);
     profile_mark(0, stream);
-    ICON_CUDA(cudaMemsetAsync(w.count, 0, sizeof(int32_t) * (NBRICK + 1), stream));
-    ICON_CUDA(cudaMemsetAsync(w.cursor, 0, sizeof(int32_t) * (NBRICK + 1), stream));
-    unsigned nblk = (unsigned)((N + 255) / 256);
+    ICON_CUDA(cudaMemsetAsync(w.count, 0, sizeof(int32_t) * (NBIN + 1), stream));
+    const unsigned nblk = (unsigned)((N + 255) / 256);
     k_points_bin<<<nblk, 256, 0, stream>>>(points, sc, sn, N, cb, w.xyz4, w.bid, w.count);
     ICON_LAUNCHED();
-    int rc = scan_exclusive_i32(w.count, w.offset, NBRICK + 1, nullptr, w.scan_ws, stream);
+    int rc = scan_exclusive_i32(w.count, w.offset, NBIN + 1, nullptr, w.scan_ws, stream);
     if (rc) return rc;
-    k_points_scatter<<<nblk, 256, 0, stream>>>(w.bid, N, w.offset, w.cursor, w.perm);
+    ICON_CUDA(cudaMemsetAsync(w.count, 0, sizeof(int32_t) * (NBIN + 1), stream));       // reuse as cursor
+    k_points_scatter<<<nblk, 256, 0, stream>>>(w.bid, N, w.offset, w.count, w.perm);
     ICON_LAUNCHED();
     static bool attr_set = false;
+    const int smem = (int)(sizeof(WarpSmem) * (SW_T / 32));
     if (!attr_set) {
-        ICON_CUDA(cudaFuncSetAttribute(k_sdf_brick, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)sizeof(BrickSmem)));
+        ICON_CUDA(cudaFuncSetAttribute(k_sdf_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
     }
     profile_mark(1, stream);
-    k_sdf_brick<<<NBRICK + 1, SDF_T, sizeof(BrickSmem), stream>>>(w.xyz4, w.perm, w.count, w.offset, m,
-                                                                  rec, face);
+    k_sdf_warp<<<(unsigned)((N + SW_T - 1) / SW_T), SW_T, smem, stream>>>(w.xyz4, w.perm, N, m, rec, face);
     ICON_LAUNCHED();
     profile_mark(2, stream);
     if (xyz4_out) *xyz4_out = w.xyz4;
@@ -407,6 +432,14 @@ int run_points_only(const float *points, int64_t sc, int64_t sn, int64_t N, cons
 }  // namespace icon
 
 using namespace icon;
+
+#ifdef ICON_SDF_STATS
+extern "C" int icon_debug_sdf_stats(unsigned long long *out, int reset) {
+    cudaMemcpyFromSymbol(out, icon::g_stats, sizeof(unsigned long long) * 8);
+    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(icon::g_stats, z, sizeof(z)); }
+    return 0;
+}
+#endif
 
 extern "C" int icon_sdf_only(const float *points, int64_t stride_c, int64_t stride_n, int64_t N,
                              const float *h_calib, const void *mesh_ws, int V, int F, float *rec,

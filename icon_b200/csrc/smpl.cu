@@ -1,59 +1,95 @@
-// SMPL body preparation: vertex normals + per-face records.  Compiled with -fmad=false.
+// SMPL body preparation: vertex normals, per-face records, Morton-ordered implicit AABB tree and
+// the yz ray grid.  Compiled with -fmad=false.
 //
 // Replaces the per-query preamble of cal_sdf_batch (lib/dataset/mesh_util.py:367-372):
 //   normals = Meshes(verts, faces).verts_normals_padded()          (pytorch3d)
 //   triangles / normals / cmaps / vis = face_vertices(., faces)    (render_utils.py:149-163)
-// which the reference recomputes on every query() call; here it runs once per body.
+// which the reference recomputes on every query() call; here it runs once per body.  The
+// acceleration structures only decide WHICH faces a query point looks at; distances, signs and
+// attributes always come from the per-face records in original face order.
+#include <float.h>
+
 #include "common.cuh"
 #include "geom.cuh"
 
 namespace icon {
 
+static void bvh_levels(int F, int &nlevels, int *cnt, int *off) {
+    int n = (F + 3) / 4, l = 0, o = 0;
+    while (true) {
+        cnt[l] = n; off[l] = o; o += n; ++l;
+        if (n == 1 || l == BVH_MAX_LEVELS) break;
+        n = (n + 3) / 4;
+    }
+    nlevels = l;
+}
+
+static MeshView carve_mesh(Carver &c, int V, int F) {
+    MeshView m{};
+    m.V = V; m.F = F;
+    bvh_levels(F, m.nlevels, m.lvl_cnt, m.lvl_off);
+    const size_t total_nodes = (size_t)m.lvl_off[m.nlevels - 1] + m.lvl_cnt[m.nlevels - 1];
+    m.tri = c.take<float4>((size_t)F * 3);
+    m.sph = c.take<float4>((size_t)F);
+    m.attr = c.take<float4>((size_t)F * 6);
+    m.rbox = c.take<float4>((size_t)F * 2);
+    m.keys = c.take<unsigned long long>((size_t)F);
+    m.order = c.take<int32_t>((size_t)F);
+    m.tri_s = c.take<float4>((size_t)F * 3);
+    m.sph_s = c.take<float4>((size_t)F);
+    m.nodes = c.take<float4>(total_nodes * 2);
+    m.rcount = c.take<int32_t>(RAY_GRID * RAY_GRID + 1);
+    m.roff = c.take<int32_t>(RAY_GRID * RAY_GRID + 1);
+    m.rlist = c.take<int32_t>((size_t)F * RAY_LIST_PER_FACE);
+    m.hdr = c.take<MeshHeader>(1);
+    m.scan_ws = c.take<char>(scan_ws_bytes(RAY_GRID * RAY_GRID + 1));
+    m.vnormals = c.take<float>((size_t)V * 3);      // last: tests read it from the tail
+    return m;
+}
+
 size_t mesh_ws_bytes(int V, int F) {
     Carver c(nullptr);
-    c.take<float4>((size_t)F * 3);
-    c.take<float4>((size_t)F);
-    c.take<float4>((size_t)F * 6);
-    c.take<float4>((size_t)F * 2);
-    c.take<float>((size_t)V * 3);
+    carve_mesh(c, V, F);
     return c.total();
 }
 
 MeshView mesh_view(const void *ws, int V, int F) {
     Carver c((void *)ws);
-    MeshView m;
-    m.tri = c.take<float4>((size_t)F * 3);
-    m.sph = c.take<float4>((size_t)F);
-    m.attr = c.take<float4>((size_t)F * 6);
-    m.rbox = c.take<float4>((size_t)F * 2);
-    m.vnormals = c.take<float>((size_t)V * 3);
-    m.V = V;
-    m.F = F;
-    return m;
+    return carve_mesh(c, V, F);
 }
 
 // pytorch3d verts_normals_packed: three sequential index_add passes (corner 1, 2, 0), each in
 // face order, then normalize(eps=1e-6).  One thread per vertex walks the face list in that
 // exact order, so the fp32 sum is bit-identical to the sequential CPU evaluation
-// (oracle_vertex_normals) -- no atomics, deterministic.
-__global__ void k_vertex_normals(const float *__restrict__ verts, const int64_t *__restrict__ faces,
-                                 int V, int F, float *__restrict__ out) {
-    int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= V) return;
+// (oracle_vertex_normals) -- no atomics, deterministic.  Faces are staged through shared memory.
+__global__ void __launch_bounds__(128) k_vertex_normals(const float *__restrict__ verts,
+                                                        const int64_t *__restrict__ faces, int V, int F,
+                                                        float *__restrict__ out) {
+    __shared__ int s_faces[3 * 512];
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
     float sx = 0.f, sy = 0.f, sz = 0.f;
     for (int pass = 0; pass < 3; ++pass) {
-        int corner = (pass == 0) ? 1 : (pass == 1 ? 2 : 0);
-        int c1 = (corner + 1) % 3, c2 = (corner + 2) % 3;
-        for (int f = 0; f < F; ++f) {
-            if (__ldg(faces + 3 * f + corner) != (int64_t)v) continue;
-            int64_t i1 = __ldg(faces + 3 * f + c1), i2 = __ldg(faces + 3 * f + c2);
-            V3 p0 = mk3(verts[3 * v], verts[3 * v + 1], verts[3 * v + 2]);
-            V3 p1 = mk3(verts[3 * i1], verts[3 * i1 + 1], verts[3 * i1 + 2]);
-            V3 p2 = mk3(verts[3 * i2], verts[3 * i2 + 1], verts[3 * i2 + 2]);
-            V3 n = cross3(sub3(p1, p0), sub3(p2, p0));
-            sx += n.x; sy += n.y; sz += n.z;
+        const int corner = (pass == 0) ? 1 : (pass == 1 ? 2 : 0);
+        const int c1 = (corner + 1) % 3, c2 = (corner + 2) % 3;
+        for (int f0 = 0; f0 < F; f0 += 512) {
+            const int nf = min(512, F - f0);
+            __syncthreads();
+            for (int k = threadIdx.x; k < 3 * nf; k += blockDim.x) s_faces[k] = (int)faces[3 * (size_t)f0 + k];
+            __syncthreads();
+            if (v < V) {
+                for (int k = 0; k < nf; ++k) {
+                    if (s_faces[3 * k + corner] != v) continue;
+                    const int i1 = s_faces[3 * k + c1], i2 = s_faces[3 * k + c2];
+                    V3 p0 = mk3(verts[3 * v], verts[3 * v + 1], verts[3 * v + 2]);
+                    V3 p1 = mk3(verts[3 * i1], verts[3 * i1 + 1], verts[3 * i1 + 2]);
+                    V3 p2 = mk3(verts[3 * i2], verts[3 * i2 + 1], verts[3 * i2 + 2]);
+                    V3 n = cross3(sub3(p1, p0), sub3(p2, p0));
+                    sx += n.x; sy += n.y; sz += n.z;
+                }
+            }
         }
     }
+    if (v >= V) return;
     float nrm = sqrtf(sx * sx + sy * sy + sz * sz);
     if (nrm < 1e-6f) nrm = 1e-6f;
     out[3 * v] = sx / nrm;
@@ -61,10 +97,19 @@ __global__ void k_vertex_normals(const float *__restrict__ verts, const int64_t 
     out[3 * v + 2] = sz / nrm;
 }
 
+__device__ __forceinline__ unsigned expand10(unsigned v) {
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+
 __global__ void k_face_records(const float *__restrict__ verts, const int64_t *__restrict__ faces,
                                const float *__restrict__ vnormals, const float *__restrict__ cmap,
                                const float *__restrict__ vis, int F, float4 *__restrict__ tri,
-                               float4 *__restrict__ sph, float4 *__restrict__ attr, float4 *__restrict__ rbox) {
+                               float4 *__restrict__ sph, float4 *__restrict__ attr, float4 *__restrict__ rbox,
+                               unsigned long long *__restrict__ keys) {
     int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= F) return;
     int64_t i0 = faces[3 * f], i1 = faces[3 * f + 1], i2 = faces[3 * f + 2];
@@ -72,8 +117,8 @@ __global__ void k_face_records(const float *__restrict__ verts, const int64_t *_
     V3 b = mk3(verts[3 * i1], verts[3 * i1 + 1], verts[3 * i1 + 2]);
     V3 c = mk3(verts[3 * i2], verts[3 * i2 + 1], verts[3 * i2 + 2]);
     V3 ab = sub3(b, a), ac = sub3(c, a);
-    // bounding sphere (centroid, max corner distance, inflated): only used as a conservative
-    // lower bound for pruning, never for the reported distance
+    // bounding sphere (centroid, max corner distance, inflated): only a conservative lower bound
+    // for pruning, never the reported distance
     V3 sc = mk3((a.x + b.x + c.x) / 3.f, (a.y + b.y + c.y) / 3.f, (a.z + b.z + c.z) / 3.f);
     float ra = dot3(sub3(a, sc), sub3(a, sc)), rb = dot3(sub3(b, sc), sub3(b, sc)),
           rc = dot3(sub3(c, sc), sub3(c, sc));
@@ -92,7 +137,123 @@ __global__ void k_face_records(const float *__restrict__ verts, const int64_t *_
     attr[6 * f + 5] = make_float4(vis[i2], 0.f, 0.f, 0.f);
     rbox[2 * f + 0] = make_float4(fminf(a.y, fminf(b.y, c.y)), fmaxf(a.y, fmaxf(b.y, c.y)),
                                   fminf(a.z, fminf(b.z, c.z)), fmaxf(a.z, fmaxf(b.z, c.z)));
-    rbox[2 * f + 1] = make_float4(fmaxf(a.x, fmaxf(b.x, c.x)), 0.f, 0.f, 0.f);
+    rbox[2 * f + 1] = make_float4(fmaxf(a.x, fmaxf(b.x, c.x)), fminf(a.x, fminf(b.x, c.x)), 0.f, 0.f);
+    // 30-bit Morton code of the centroid over [-1.5, 1.5]^3
+    auto qz = [](float v) { return (unsigned)fminf(fmaxf((v + 1.5f) * (1024.f / 3.f), 0.f), 1023.f); };
+    unsigned code = (expand10(qz(sc.x)) << 2) | (expand10(qz(sc.y)) << 1) | expand10(qz(sc.z));
+    keys[f] = ((unsigned long long)code << 32) | (unsigned)f;
+}
+
+// rank sort: F is ~1e4, so F^2 comparisons from shared memory are cheaper than a radix sort's passes
+__global__ void __launch_bounds__(256) k_rank_sort(const unsigned long long *__restrict__ keys, int F,
+                                                   int32_t *__restrict__ order) {
+    __shared__ unsigned long long tile[1024];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long my = i < F ? keys[i] : 0ull;
+    int rank = 0;
+    for (int j0 = 0; j0 < F; j0 += 1024) {
+        const int n = min(1024, F - j0);
+        __syncthreads();
+        for (int k = threadIdx.x; k < n; k += 256) tile[k] = keys[j0 + k];
+        __syncthreads();
+        if (i < F)
+            for (int k = 0; k < n; ++k) rank += tile[k] < my;
+    }
+    if (i < F) order[rank] = i;
+}
+
+// sorted copies + leaf boxes (level 0), then the upper levels inside one CTA
+__global__ void k_sorted_copy(const int32_t *__restrict__ order, const float4 *__restrict__ tri,
+                              const float4 *__restrict__ sph, int F, float4 *__restrict__ tri_s,
+                              float4 *__restrict__ sph_s) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= F) return;
+    const int f = order[p];
+    tri_s[3 * p] = tri[3 * f]; tri_s[3 * p + 1] = tri[3 * f + 1]; tri_s[3 * p + 2] = tri[3 * f + 2];
+    float4 s = sph[f];
+    sph_s[p] = s;
+}
+
+__global__ void __launch_bounds__(1024) k_build_tree(const float4 *__restrict__ tri_s, MeshView m) {
+    // level 0: leaf = 4 consecutive sorted faces
+    for (int n = threadIdx.x; n < m.lvl_cnt[0]; n += blockDim.x) {
+        float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+        for (int t = 4 * n; t < min(4 * n + 4, m.F); ++t) {
+            Tri tr = load_tri(tri_s + 3 * (size_t)t);
+            const V3 vs[3] = {tr.a, mk3(tr.a.x + tr.ab.x, tr.a.y + tr.ab.y, tr.a.z + tr.ab.z),
+                              mk3(tr.a.x + tr.ac.x, tr.a.y + tr.ac.y, tr.a.z + tr.ac.z)};
+            for (int k = 0; k < 3; ++k) {
+                lo[0] = fminf(lo[0], vs[k].x); hi[0] = fmaxf(hi[0], vs[k].x);
+                lo[1] = fminf(lo[1], vs[k].y); hi[1] = fmaxf(hi[1], vs[k].y);
+                lo[2] = fminf(lo[2], vs[k].z); hi[2] = fmaxf(hi[2], vs[k].z);
+            }
+        }
+        m.nodes[2 * (size_t)n] = make_float4(lo[0], lo[1], lo[2], 0.f);
+        m.nodes[2 * (size_t)n + 1] = make_float4(hi[0], hi[1], hi[2], 0.f);
+    }
+    for (int l = 1; l < m.nlevels; ++l) {
+        __threadfence_block();
+        __syncthreads();
+        for (int n = threadIdx.x; n < m.lvl_cnt[l]; n += blockDim.x) {
+            float4 lo = make_float4(FLT_MAX, FLT_MAX, FLT_MAX, 0.f), hi = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, 0.f);
+            for (int c = 4 * n; c < min(4 * n + 4, m.lvl_cnt[l - 1]); ++c) {
+                float4 a = m.nodes[2 * ((size_t)m.lvl_off[l - 1] + c)], b = m.nodes[2 * ((size_t)m.lvl_off[l - 1] + c) + 1];
+                lo.x = fminf(lo.x, a.x); lo.y = fminf(lo.y, a.y); lo.z = fminf(lo.z, a.z);
+                hi.x = fmaxf(hi.x, b.x); hi.y = fmaxf(hi.y, b.y); hi.z = fmaxf(hi.z, b.z);
+            }
+            m.nodes[2 * ((size_t)m.lvl_off[l] + n)] = lo;
+            m.nodes[2 * ((size_t)m.lvl_off[l] + n) + 1] = hi;
+        }
+    }
+    // ray grid frame from the root box
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const size_t root = (size_t)m.lvl_off[m.nlevels - 1];
+        float4 lo = m.nodes[2 * root], hi = m.nodes[2 * root + 1];
+        const float pad = 1e-3f;
+        MeshHeader h;
+        h.y0 = lo.y - pad; h.z0 = lo.z - pad;
+        h.inv_cy = (float)RAY_GRID / ((hi.y + pad) - h.y0);
+        h.inv_cz = (float)RAY_GRID / ((hi.z + pad) - h.z0);
+        h.ray_overflow = 0;
+        h.pad[0] = h.pad[1] = h.pad[2] = 0;
+        *m.hdr = h;
+    }
+}
+
+// ---- yz cell lists for the +x ray: a face is listed in every cell its (inflated) yz box overlaps
+__device__ __forceinline__ void cell_range(const MeshHeader &h, float4 rb, int &cy0, int &cy1, int &cz0, int &cz1) {
+    const float e = 1e-4f;
+    cy0 = max(0, min(RAY_GRID - 1, (int)floorf((rb.x - e - h.y0) * h.inv_cy)));
+    cy1 = max(0, min(RAY_GRID - 1, (int)floorf((rb.y + e - h.y0) * h.inv_cy)));
+    cz0 = max(0, min(RAY_GRID - 1, (int)floorf((rb.z - e - h.z0) * h.inv_cz)));
+    cz1 = max(0, min(RAY_GRID - 1, (int)floorf((rb.w + e - h.z0) * h.inv_cz)));
+}
+
+__global__ void k_ray_count(MeshView m) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= m.F) return;
+    const MeshHeader h = *m.hdr;
+    int cy0, cy1, cz0, cz1;
+    cell_range(h, m.rbox[2 * (size_t)f], cy0, cy1, cz0, cz1);
+    for (int cz = cz0; cz <= cz1; ++cz)
+        for (int cy = cy0; cy <= cy1; ++cy) atomicAdd(&m.rcount[cz * RAY_GRID + cy], 1);
+}
+
+__global__ void k_ray_fill(MeshView m, int32_t *__restrict__ cursor) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= m.F) return;
+    const MeshHeader h = *m.hdr;
+    int cy0, cy1, cz0, cz1;
+    cell_range(h, m.rbox[2 * (size_t)f], cy0, cy1, cz0, cz1);
+    const int cap = m.F * RAY_LIST_PER_FACE;
+    for (int cz = cz0; cz <= cz1; ++cz)
+        for (int cy = cy0; cy <= cy1; ++cy) {
+            const int c = cz * RAY_GRID + cy;
+            const int pos = m.roff[c] + atomicAdd(&cursor[c], 1);
+            if (pos < cap) m.rlist[pos] = f;
+            else m.hdr->ray_overflow = 1;
+        }
 }
 
 }  // namespace icon
@@ -106,18 +267,33 @@ extern "C" int icon_smpl_prepare(const float *verts, const int64_t *faces, const
                                  icon_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     ICON_CHECK_ARG(V > 0 && F > 0, "icon_smpl_prepare: empty mesh (V=%d F=%d)", V, F);
+    ICON_CHECK_ARG(F <= 4 * 65535, "icon_smpl_prepare: F=%d too large (leaf ids are 16-bit)", F);
     ICON_CHECK_ARG(verts && faces && cmap && vis && mesh_ws, "icon_smpl_prepare: null pointer");
     if (mesh_ws_bytes_ < mesh_ws_bytes(V, F)) {
         set_error("icon_smpl_prepare: workspace %zu < %zu", mesh_ws_bytes_, mesh_ws_bytes(V, F));
         return ICON_ENOSPC;
     }
-    MeshView m = mesh_view(mesh_ws, V, F);
+    Carver c(mesh_ws);
+    MeshView m = carve_mesh(c, V, F);
+    void *scan_ws = m.scan_ws;
     k_vertex_normals<<<(V + 127) / 128, 128, 0, stream>>>(verts, faces, V, F, m.vnormals);
     ICON_LAUNCHED();
-    k_face_records<<<(F + 127) / 128, 128, 0, stream>>>(verts, faces, m.vnormals, cmap, vis, F,
-                                                        (float4 *)m.tri, (float4 *)m.sph,
-                                                        (float4 *)m.attr,
-                                                        (float4 *)m.rbox);
+    k_face_records<<<(F + 127) / 128, 128, 0, stream>>>(verts, faces, m.vnormals, cmap, vis, F, (float4 *)m.tri,
+                                                        (float4 *)m.sph, (float4 *)m.attr, (float4 *)m.rbox, m.keys);
+    ICON_LAUNCHED();
+    k_rank_sort<<<(F + 255) / 256, 256, 0, stream>>>(m.keys, F, m.order);
+    ICON_LAUNCHED();
+    k_sorted_copy<<<(F + 127) / 128, 128, 0, stream>>>(m.order, m.tri, m.sph, F, m.tri_s, m.sph_s);
+    ICON_LAUNCHED();
+    k_build_tree<<<1, 1024, 0, stream>>>(m.tri_s, m);
+    ICON_LAUNCHED();
+    ICON_CUDA(cudaMemsetAsync(m.rcount, 0, sizeof(int32_t) * (RAY_GRID * RAY_GRID + 1), stream));
+    k_ray_count<<<(F + 127) / 128, 128, 0, stream>>>(m);
+    ICON_LAUNCHED();
+    int rc = scan_exclusive_i32(m.rcount, m.roff, RAY_GRID * RAY_GRID + 1, nullptr, scan_ws, stream);
+    if (rc) return rc;
+    ICON_CUDA(cudaMemsetAsync(m.rcount, 0, sizeof(int32_t) * (RAY_GRID * RAY_GRID + 1), stream));   // reuse as cursor
+    k_ray_fill<<<(F + 127) / 128, 128, 0, stream>>>(m, m.rcount);
     ICON_LAUNCHED();
     return ICON_OK;
 }
