@@ -158,6 +158,8 @@ __device__ unsigned long long g_stats[8];   // warps, overflow warps, sum leaves
 
 struct WarpSmem {
     unsigned short fr[2][FR_CAP];      // node / leaf ids (leaf count <= 65535 is checked by the host)
+    float4 sph[32];                    // bounding spheres of the 32 faces of the current chunk
+    int kk[32];                        // their sorted positions
 };
 
 __device__ __forceinline__ float box_far2(V3 p, float4 lo, float4 hi) {   // squared distance to the farthest corner
@@ -256,43 +258,58 @@ __global__ void __launch_bounds__(SW_T) k_sdf_warp(const float4 *__restrict__ xy
     }
     STAT(0, 1); STAT(1, overflow ? 1 : 0); STAT(2, n);
     // ---- phases C+D: 32 faces (8 leaves) at a time: cull by bounding sphere against the warp bound,
-    //      then every lane tests the survivors against its own best
+    //      then every lane tests the survivors against its own best through two cheap lower bounds
+    //      (bounding sphere, then the support-function bound d >= |w| - max_k u.(v_k - c_f), u = w/|w|,
+    //      w = p - c_f, which is nearly exact for faces seen head-on) before the exact distance.
     {
-        float sb = sqrtf(best);
-        auto lane_test = [&](int k) {
-            const float4 s = __ldg(m.sph_s + k);
+        float sbA = best * rsqrtf(best) * 1.00001f + 1e-6f;    // ~sqrt(best), inflated; bounds only
+        auto lane_test = [&](int k, float4 s) {
             const float dx = p.x - s.x, dy = p.y - s.y, dz = p.z - s.z;
             const float dd = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-            const float l = sb + s.w + 1e-6f;
-            if (dd > l * l * 1.00001f) return;                 // sphere lower bound beats this lane's best
-            const float before = best;
-            try_face(k);
-            if (best != before) sb = sqrtf(best);
+            const float l = sbA + s.w;
+            if (dd > l * l) return;                            // sphere bound beats this lane's best
+            const Tri tr = load_tri(m.tri_s + 3 * (size_t)k);
+            const float S1 = fmaf(dz, tr.ab.z, fmaf(dy, tr.ab.y, dx * tr.ab.x));
+            const float T1 = fmaf(dz, tr.ac.z, fmaf(dy, tr.ac.y, dx * tr.ac.x));
+            const float M = fmaxf(fmaxf(-(S1 + T1), fmaf(2.f, S1, -T1)), fmaf(2.f, T1, -S1)) * (1.f / 3.f);
+            const float g = dd - M - 1e-7f;                    // |w|^2 - |w| h(u)
+            if (g > 0.f && g * g > best * dd * 1.0001f) return;   // support bound beats this lane's best
+            const float d = tri_sqdist(p, tr.a, tr.ab, tr.ac);
+            const int f = __ldg(m.order + k);
+            if (d < best || (d == best && f < bi)) {
+                best = d; bi = f;
+                sbA = d * rsqrtf(d) * 1.00001f + 1e-6f;
+                if (!(d > 0.f)) sbA = 1e-6f;
+            }
         };
         if (!overflow) {
             for (int base = 0; base < n; base += 8) {
                 const int slot = base + (lane >> 2);
                 bool pass = false;
                 int k = 0;
+                float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (slot < n) {
                     k = 4 * (int)S.fr[cur][slot] + (lane & 3);
                     if (k < m.F) {
-                        const float4 s = __ldg(m.sph_s + k);
+                        s = __ldg(m.sph_s + k);
                         const float dx = c.x - s.x, dy = c.y - s.y, dz = c.z - s.z;
                         const float l2 = lim + s.w;
                         pass = fmaf(dz, dz, fmaf(dy, dy, dx * dx)) <= l2 * l2;
                     }
                 }
+                S.sph[lane] = s;
+                S.kk[lane] = k;
                 unsigned mask = __ballot_sync(0xffffffffu, pass);
                 STAT(3, __popc(mask));
                 while (mask) {
                     const int src = __ffs(mask) - 1;
                     mask &= mask - 1;
-                    lane_test(__shfl_sync(0xffffffffu, k, src));
+                    lane_test(S.kk[src], S.sph[src]);
                 }
+                __syncwarp();
             }
         } else {
-            for (int k = 0; k < m.F; ++k) lane_test(k);
+            for (int k = 0; k < m.F; ++k) lane_test(k, __ldg(m.sph_s + k));
         }
     }
     // ---- +x ray parity
