@@ -27,6 +27,7 @@ if ROOT not in sys.path:
 
 GRID = 256
 MLP_FLOP_PER_POINT = 344602          # BASELINE.md section 2 (c0 = 13)
+TRAFFIC_MLP_BYTES = None             # filled from the committed ncu capture (profiles/), bytes per launch
 WORKLOAD = "icon-filter, dense 256^3 cell-centre lattice (16,777,216 points), 1 image per GPU"
 
 
@@ -267,7 +268,7 @@ def main():
         value = total_pts / (ms * 1e-3) / 1e6
         e2e = total_pts / (ms_e2e * 1e-3) / 1e6
         mlp_ms, sdf_ms = stage[3], stage[1]
-        dom = "k_query_mlp" if mlp_ms >= sdf_ms else "k_sdf_brick"
+        dom = "k_query_mlp_tc" if mlp_ms >= sdf_ms else "k_sdf_warp"
         achieved = N * MLP_FLOP_PER_POINT / (mlp_ms * 1e-3) / 1e12
         line = {
             "metric": "M query-points/sec at 256^3 grid", "value": value, "unit": "Mpoints/s",
@@ -282,13 +283,16 @@ def main():
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "stages_ms": {"bin_sort": stage[0], "sdf_brick": stage[1], "outlier_rank": stage[2],
+            "stages_ms": {"bin_sort": stage[0], "sdf_warp": stage[1], "outlier_rank": stage[2],
                           "gather_mlp": stage[3], "dominant": dom},
-            "roofline": {"kernel": "k_query_mlp<icon>", "bound": "tensor", "achieved": achieved,
-                         "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
-                         "traffic": None, "peak_source": peaks["src"] + " bf16 burst (cuBLAS)",
-                         "note": "algorithmic MLP FLOPs (344,602/pt) / CUDA-event kernel time; "
-                                 "this round's kernel runs the MLP on the FP32 FMA pipe"},
+            "roofline": {"kernel": "k_query_mlp_tc<icon> (tcgen05, fp16 hi/lo x3)", "bound": "tensor",
+                         "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                         "frac": achieved / peaks["bf16_tflops"], "traffic": TRAFFIC_MLP_BYTES,
+                         "executed_tflops": 3.0 * achieved, "executed_frac": 3.0 * achieved / peaks["bf16_tflops"],
+                         "peak_source": peaks["src"] + " bf16 burst (cuBLAS), kernel timed alone with CUDA events",
+                         "note": "achieved = algorithmic MLP FLOPs (344,602/pt x points) / kernel time; the kernel "
+                                 "executes 3 fp16 MMAs per algorithmic one to hold 1e-4 (executed_*); traffic = "
+                                 "dram read+write bytes per launch from profiles/ (ncu --set full)"},
             "checksum": checksum,
         }
         if not args.no_cpu_baseline and world == 1:

@@ -42,6 +42,13 @@ _SIGS = {
     "icon_grid_scatter": (_i, [_vp, _vp, _vp, _i64, _vp]),
     "icon_grid_init_points": (_i, [_i, _i, _vp, _vp, _vp, _vp]),
     "icon_grid_count_above": (_i, [_vp, _i64, _f, _vp, _vp]),
+    "icon_conv2d": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "icon_group_norm": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp]),
+    "icon_avg_pool2": (_i, [_vp, _vp, _i64, _i, _i, _vp]),
+    "icon_bicubic_up2_add": (_i, [_vp, _vp, _vp, _i64, _i, _i, _vp]),
+    "icon_cat3_add": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i64, _vp]),
+    "icon_add3": (_i, [_vp, _vp, _vp, _vp, _i64, _vp]),
+    "icon_normalize_mask": (_i, [_vp, _vp, _vp, _i, _i, _i64, _vp]),
     "icon_mc_workspace_bytes": (_sz, [_i, _i]),
     "icon_mc_count": (_i, [_vp, _i, _f, _i, _vp, _sz, _vp, _vp]),
     "icon_mc_emit": (_i, [_vp, _i, _f, _i, _vp, _vp, _vp, _i64, _i64, _vp]),

@@ -171,6 +171,33 @@ int icon_mc_count(const float *occ, int R, float iso, int padded, void *ws, size
 int icon_mc_emit(const float *occ, int R, float iso, int padded, const void *ws, void *verts,
                  int64_t *faces, int64_t n_verts, int64_t n_tris, icon_stream_t stream);
 
+/* ------------------------------------------------------------------ encoder operators (NCHW fp32)
+ * Replace the cuDNN / torch calls inside HGFilter (lib/net/HGFilters.py:161-197, ConvBlock
+ * lib/net/net_util.py:258-280), GlobalGenerator / ResnetBlock (lib/net/FBNet.py:216-319) and
+ * NormalNet.forward (lib/net/NormalNet.py:84-97).
+ * icon_conv2d: nn.Conv2d (zero padding, or reflect = ReflectionPad2d(pad) folded in) or, with
+ * transposed = 1, nn.ConvTranspose2d(stride, padding = pad, output_padding = out_pad); weights in
+ * torch layout; optional bias, residual add and activation (0 none, 1 ReLU, 2 tanh) in the epilogue.
+ * icon_group_norm: nn.GroupNorm(groups, C) with affine (gamma, beta), or nn.InstanceNorm2d(C) when
+ * groups == C and gamma == beta == NULL; optional residual add and ReLU fused. */
+int icon_conv2d(const float *x, const float *w, const float *bias, const float *res, float *y, int N, int Cin,
+                int H, int W, int Cout, int KH, int KW, int stride, int pad, int out_pad, int reflect,
+                int transposed, int act, icon_stream_t stream);
+int icon_group_norm(const float *x, const float *gamma, const float *beta, const float *res, float *y, int N,
+                    int C, int HW, int groups, float eps, int relu, icon_stream_t stream);
+/* F.avg_pool2d(x, 2, stride=2); planes = N*C */
+int icon_avg_pool2(const float *x, float *y, int64_t planes, int H, int W, icon_stream_t stream);
+/* y = add + F.interpolate(x, scale_factor=2, mode="bicubic", align_corners=True) (HGFilters.py:70-76) */
+int icon_bicubic_up2_add(const float *x, const float *add, float *y, int64_t planes, int H, int W,
+                         icon_stream_t stream);
+/* y = cat(a, b, c, dim=1) + res (ConvBlock, net_util.py:273-278) */
+int icon_cat3_add(const float *a, const float *b, const float *c, const float *res, float *y, int N, int C1, int C2,
+                  int C3, int64_t HW, icon_stream_t stream);
+int icon_add3(const float *a, const float *b, const float *c, float *y, int64_t n, icon_stream_t stream);
+/* y = x / ||x||_2 (over 3 channels, no eps) * (sum_c |image| != 0)  (NormalNet.py:88-97) */
+int icon_normalize_mask(const float *x, const float *image, float *y, int N, int Cimg, int64_t HW,
+                        icon_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,142 @@
+"""Encoder kernels (csrc/conv.cu) against torch's CPU operators and against outputs of the
+reference's own HGFilter / GlobalGenerator (tests/golden/encoders.npz, reference imported live)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from icon_b200 import synthetic as S  # noqa: E402
+
+
+def _cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+def _g(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+@pytest.mark.parametrize("cin,cout,k,s,p,reflect,hw", [
+    (3, 64, 7, 2, 3, 0, 64), (64, 64, 3, 1, 1, 0, 33), (128, 256, 1, 1, 0, 0, 16), (6, 64, 7, 1, 3, 3, 40),
+    (32, 32, 3, 1, 1, 1, 24), (64, 128, 3, 2, 1, 0, 32), (64, 3, 7, 1, 3, 3, 32), (256, 6, 1, 1, 0, 0, 20)])
+def test_conv2d_matches_torch(cin, cout, k, s, p, reflect, hw):
+    dev = _cuda()
+    from icon_b200 import conv_ops as C
+    conv = nn.Conv2d(cin, cout, k, stride=s, padding=0 if reflect else p)
+    x = torch.randn(2, cin, hw, hw + 3, generator=_g(cin + cout))
+    with torch.no_grad():
+        ref = conv(F.pad(x, (reflect,) * 4, mode="reflect") if reflect else x)
+        res = torch.randn(ref.shape, generator=_g(7))
+        ref_r = torch.tanh(ref + res)
+    y = C.conv2d(x.to(dev), conv.to(dev), reflect=reflect)
+    assert y.shape == ref.shape
+    assert (y.cpu() - ref).abs().max() <= 2e-5 * max(1.0, ref.abs().max().item())
+    y2 = C.conv2d(x.to(dev), conv, reflect=reflect, tanh=True, residual=res.to(dev))
+    assert (y2.cpu() - ref_r).abs().max() <= 2e-5
+
+
+def test_conv_transpose2d_matches_torch():
+    dev = _cuda()
+    from icon_b200 import conv_ops as C
+    ct = nn.ConvTranspose2d(48, 24, 3, stride=2, padding=1, output_padding=1)
+    x = torch.randn(2, 48, 17, 19, generator=_g(1))
+    with torch.no_grad():
+        ref = ct(x)
+    y = C.conv_transpose2d(x.to(dev), ct.to(dev))
+    assert y.shape == ref.shape
+    assert (y.cpu() - ref).abs().max() <= 2e-5
+
+
+def test_norms_pool_bicubic_joins_match_torch():
+    dev = _cuda()
+    from icon_b200 import conv_ops as C
+    x = torch.randn(2, 64, 24, 20, generator=_g(2)) * 2 + 0.5
+    gn = nn.GroupNorm(32, 64)
+    with torch.no_grad():
+        gn.weight.copy_(1 + 0.1 * torch.randn(64, generator=_g(3)))
+        gn.bias.copy_(0.1 * torch.randn(64, generator=_g(4)))
+        ref = F.relu(gn(x))
+    assert (C.group_norm(x.to(dev), gn.to(dev), relu=True).cpu() - ref).abs().max() <= 2e-5
+    inorm = nn.InstanceNorm2d(64, affine=False)
+    with torch.no_grad():
+        ref_i = F.relu(inorm(x))
+        ref_res = x + inorm(x * 0.5 + 1)
+    assert (C.instance_norm(x.to(dev), relu=True).cpu() - ref_i).abs().max() <= 2e-5
+    assert (C.instance_norm((x * 0.5 + 1).to(dev), residual=x.to(dev)).cpu() - ref_res).abs().max() <= 2e-5
+    assert torch.equal(C.avg_pool2(x.to(dev)).cpu(), F.avg_pool2d(x, 2, stride=2)) or \
+        (C.avg_pool2(x.to(dev)).cpu() - F.avg_pool2d(x, 2, stride=2)).abs().max() <= 1e-6
+    lo = torch.randn(1, 8, 9, 11, generator=_g(5))
+    up1 = torch.randn(1, 8, 18, 22, generator=_g(6))
+    ref_b = up1 + F.interpolate(lo, scale_factor=2, mode="bicubic", align_corners=True)
+    assert (C.bicubic_up2_add(lo.to(dev), up1.to(dev)).cpu() - ref_b).abs().max() <= 2e-5
+    a, b, c = (torch.randn(2, n, 6, 5, generator=_g(n)) for n in (8, 4, 4))
+    r = torch.randn(2, 16, 6, 5, generator=_g(9))
+    assert torch.equal(C.cat_add((a.to(dev), b.to(dev), c.to(dev)), r.to(dev)).cpu(), torch.cat((a, b, c), 1) + r)
+    assert torch.equal(C.add3(a.to(dev), a.to(dev) * 2, a.to(dev) * 3).cpu(), a + a * 2 + a * 3)
+    nml = torch.randn(1, 3, 10, 10, generator=_g(10))
+    img = torch.randn(1, 3, 10, 10, generator=_g(11))
+    img[:, :, :3] = 0
+    ref_n = nml / torch.norm(nml, dim=1, keepdim=True) * (img.abs().sum(1, keepdim=True) != 0).float()
+    assert (C.normalize_mask(nml.to(dev), img.to(dev)).cpu() - ref_n).abs().max() <= 1e-6
+
+
+def test_hgfilter_matches_reference_module(golden_dir):
+    dev = _cuda()
+    from icon_b200 import config
+    from icon_b200.encoders import HGFilter
+    g = np.load(os.path.join(golden_dir, "encoders.npz"))
+    cfg = config.preset("icon-filter")
+    hg = HGFilter(cfg.net, 2, 3)
+    hg.load_state_dict(S.seeded_like(hg.state_dict(), 21))
+    hg = hg.to(dev).eval()
+    y = hg(torch.from_numpy(g["hg_x"]).to(dev))
+    assert len(y) == 2 and tuple(y[-1].shape) == tuple(g["hg_y"].shape)
+    err = np.abs(y[-1].cpu().numpy() - g["hg_y"]).max()
+    assert err <= 2e-4 * max(1.0, np.abs(g["hg_y"]).max()), err
+
+
+def test_global_generator_matches_reference_module(golden_dir):
+    dev = _cuda()
+    from icon_b200.encoders import GlobalGenerator
+    g = np.load(os.path.join(golden_dir, "encoders.npz"))
+    gg = GlobalGenerator(6, 3, 64, 4, 9)
+    gg.load_state_dict(S.seeded_like(gg.state_dict(), 22))
+    gg = gg.to(dev).eval()
+    y = gg(torch.from_numpy(g["gg_x"]).to(dev))
+    err = np.abs(y.cpu().numpy() - g["gg_y"]).max()
+    assert tuple(y.shape) == tuple(g["gg_y"].shape)
+    assert err <= 2e-4, err
+
+
+def test_filter_icon_filter_config_shapes_and_timing():
+    """HGPIFuNet.filter on the BASELINE config (icon-filter, 512x512): NormalNet + 2 x HGFilter."""
+    dev = _cuda()
+    from icon_b200 import config, net
+    cfg = config.preset("icon-filter")
+    netG = net.HGPIFuNet(cfg).to(dev).eval()
+    g = _g(0)
+    batch = {"image": torch.rand(1, 3, 512, 512, generator=g).to(dev) * 2 - 1,
+             "T_normal_F": torch.rand(1, 3, 512, 512, generator=g).to(dev) * 2 - 1,
+             "T_normal_B": torch.rand(1, 3, 512, 512, generator=g).to(dev) * 2 - 1,
+             "smpl_verts": torch.zeros(1, 4, 3).to(dev), "smpl_faces": torch.zeros(1, 2, 3).long().to(dev),
+             "smpl_vis": torch.zeros(1, 4, 1).to(dev), "smpl_cmap": torch.zeros(1, 4, 3).to(dev)}
+    with torch.no_grad():
+        feats, inter = netG.filter(batch, return_inter=True)      # runs NormalNet (normals absent) + F_filter x2
+    assert len(feats) == 1 and tuple(feats[0].shape) == (1, 12, 128, 128)
+    assert tuple(inter.shape) == (1, 6, 512, 512)
+    assert torch.isfinite(feats[0]).all()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    with torch.no_grad():
+        netG.filter(batch)
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"filter (NormalNet + 2 x HGFilter, 512^2): {e0.elapsed_time(e1):.1f} ms")
