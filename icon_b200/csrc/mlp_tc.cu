@@ -8,14 +8,17 @@
 // hi*Whi + hi*Wlo + lo*Whi with fp32 accumulation in tensor memory -- three kind::f16 MMAs per
 // k-step, fp32-class accuracy (parity bar 1e-4 on the logit; measured error in DESIGN.md).
 //
-// One persistent CTA per SM, 128 query points (= 128 TMEM lanes) per tile, 320 threads:
+// One persistent CTA per SM, 128 query points (= 128 TMEM lanes) per tile, 448 threads:
 //   warp 0      weight producer: 1-D bulk copies (cp.async.bulk, TMA engine) of host-pre-swizzled
 //               K-major SWIZZLE_128B tiles from L2 into a 2 x 64 KB ring, mbarrier complete_tx
 //   warp 1      MMA issuer (one elected lane): tcgen05.mma.cta_group::1.kind::f16, M=128
 //   warps 2-9   workers, one TMEM lane (= query point) per thread, two threads per lane:
-//               feature gather -> x0; per 64-column chunk of layer 0: tcgen05.ld -> +bias ->
-//               LeakyReLU -> hi/lo fp16 -> tcgen05.st as the A operand (in TMEM) of layer 1; same
-//               for layer 1 -> layer 2; layer 3 (141 -> 1) as an fp32 dot product in registers.
+//               per 64-column chunk of layer 0: tcgen05.ld -> +bias -> LeakyReLU -> hi/lo fp16 ->
+//               tcgen05.st as the A operand (in TMEM) of layer 1; same for layer 1 -> layer 2 (in 4
+//               K-chunks so layer 2 starts early); layer 3 (141 -> 1) as an fp32 dot in registers.
+//   warps 10-13 gather: one query point per thread; the 16 input features of tile i+1 (bilinear /
+//               trilinear samples, SMPL record, outlier rule) are produced and published as the
+//               double-buffered x0 operand while tile i is in the tensor pipe.
 // Layer-0 chunks are issued two ahead of the layer-1 chunk that consumes them, so the tensor pipe
 // always has queued work while the workers convert.  TMEM map (512 columns):
 //   [0,256) layer-1 accumulator (later [0,128) layer-2 accumulator)
@@ -29,7 +32,7 @@
 
 namespace icon {
 
-constexpr int TC_THREADS = 320;
+constexpr int TC_THREADS = 448;      // 1 producer + 1 MMA + 8 worker + 4 gather warps
 constexpr int TC_M = 128;
 
 // byte offsets inside the packed tensor-core weight blob (host: icon_b200/ops.py pack_mlp_tc)
@@ -45,18 +48,18 @@ static_assert(TCB_BYTES == ICON_MLP_TC_BYTES, "blob layout");
 // shared memory map (bytes from a 1024-aligned base)
 constexpr int SM_STAGE = 0;                       // 2 x 65536
 constexpr int SM_W0 = 131072;                     // 32768
-constexpr int SM_X0H = SM_W0 + 32768;             // 4096  A tile of x0 (hi), no swizzle, LBO 2048, SBO 128
-constexpr int SM_X0L = SM_X0H + 4096;             // 4096
-constexpr int SM_X0F = SM_X0L + 4096;             // 2 x [16][128] fp32
+constexpr int SM_X0H = SM_W0 + 32768;             // 2 x 4096  A tile of x0 (hi), no swizzle, LBO 2048, SBO 128
+constexpr int SM_X0L = SM_X0H + 8192;             // 2 x 4096
+constexpr int SM_X0F = SM_X0L + 8192;             // 2 x [16][128] fp32
 constexpr int SM_F32 = SM_X0F + 2 * 8192;         // biases etc.
 constexpr int SM_PART = SM_F32 + TCB_F32_FLOATS * 4;   // [128] fp32 layer-3 partials
-constexpr int SM_BAR = SM_PART + 512;             // 16 mbarriers
-constexpr int SM_MISC = SM_BAR + 16 * 8;
+constexpr int SM_BAR = SM_PART + 512;             // 24 mbarriers
+constexpr int SM_MISC = SM_BAR + 24 * 8;
 constexpr int SM_TOTAL = SM_MISC + 64;
 constexpr int TC_SMEM_BYTES = SM_TOTAL + 1024;    // slack for manual 1024-B alignment
 
-enum { B_WFULL0 = 0, B_WFULL1, B_WEMPTY0, B_WEMPTY1, B_X0, B_ACC0F0, B_ACC0F1, B_A0F0, B_A0F1, B_A0E0, B_A0E1,
-       B_ACC1, B_ACT1, B_ACC2, B_W0RDY };
+enum { B_WFULL0 = 0, B_WFULL1, B_WEMPTY0, B_WEMPTY1, B_X0R0, B_X0R1, B_X0F0, B_X0F1, B_ACC0F0, B_ACC0F1, B_A0F0, B_A0F1,
+       B_A0E0, B_A0E1, B_ACC1, B_ACT1_0, B_ACT1_1, B_ACT1_2, B_ACT1_3, B_ACC2, B_W0RDY };
 
 // TMEM columns
 constexpr uint32_t T_ACC1 = 0, T_A0 = 256, T_ACC0 = 384, T_ACT1H = 256, T_ACT1L = 384, T_ACC2 = 0;
@@ -179,11 +182,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_query_mlp_tc(QueryParams q, c
     if (tid == 0) {
         mbar_init(BAR(B_WFULL0), 1); mbar_init(BAR(B_WFULL1), 1);
         mbar_init(BAR(B_WEMPTY0), 1); mbar_init(BAR(B_WEMPTY1), 1);
-        mbar_init(BAR(B_X0), 256);
+        mbar_init(BAR(B_X0R0), 128); mbar_init(BAR(B_X0R1), 128);      // gather warps -> MMA / workers
+        mbar_init(BAR(B_X0F0), 256); mbar_init(BAR(B_X0F1), 256);      // workers -> gather warps (buffer free)
         mbar_init(BAR(B_ACC0F0), 1); mbar_init(BAR(B_ACC0F1), 1);
         mbar_init(BAR(B_A0F0), 256); mbar_init(BAR(B_A0F1), 256);
         mbar_init(BAR(B_A0E0), 1); mbar_init(BAR(B_A0E1), 1);
-        mbar_init(BAR(B_ACC1), 1); mbar_init(BAR(B_ACT1), 256); mbar_init(BAR(B_ACC2), 1);
+        mbar_init(BAR(B_ACC1), 1); mbar_init(BAR(B_ACC2), 1);
+        for (int c = 0; c < 4; ++c) mbar_init(BAR(B_ACT1_0 + c), 256);
         mbar_init(BAR(B_W0RDY), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -223,9 +228,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_query_mlp_tc(QueryParams q, c
         // ======================================================== MMA issuer
         if (lane == 0) {
             constexpr uint32_t ID64 = idesc_f16(128, 64), ID256 = idesc_f16(128, 256), ID128 = idesc_f16(128, 128);
-            const uint64_t dx0h = desc_nosw(base + SM_X0H, 2048, 128), dx0l = desc_nosw(base + SM_X0L, 2048, 128);
+            const uint64_t dx0h0 = desc_nosw(base + SM_X0H, 2048, 128), dx0l0 = desc_nosw(base + SM_X0L, 2048, 128);
             const uint64_t dw0h = desc_nosw(base + SM_W0, 8192, 128), dw0l = desc_nosw(base + SM_W0 + 16384, 8192, 128);
-            uint32_t ph_x0 = 0, ph_a0f[2] = {0, 0}, ph_act1 = 0, cnt = 0;
+            uint32_t ph_x0[2] = {0, 0}, ph_a0f[2] = {0, 0}, ph_act1 = 0, cnt = 0, tcount = 0;
+            uint64_t dx0h = dx0h0, dx0l = dx0l0;
             mbar_wait(BAR(B_W0RDY), 0);
             auto L0 = [&](int j) {
                 const uint32_t d = tmem + T_ACC0 + 64u * (uint32_t)(j & 1);
@@ -235,8 +241,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_query_mlp_tc(QueryParams q, c
                 mma_ss(d, dx0l, dw0h + o, ID64, 1);
                 tc_commit(BAR(B_ACC0F0 + (j & 1)));
             };
-            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                mbar_wait(BAR(B_X0), ph_x0); ph_x0 ^= 1;
+            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+                const uint32_t xb = tcount & 1;
+                dx0h = dx0h0 + (uint64_t)(xb * 4096 / 16);
+                dx0l = dx0l0 + (uint64_t)(xb * 4096 / 16);
+                mbar_wait(BAR(B_X0R0 + xb), ph_x0[xb]); ph_x0[xb] ^= 1;
                 tc_fence_after();
                 L0(0);
                 L0(1);
@@ -259,9 +268,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_query_mlp_tc(QueryParams q, c
                     if (j + 2 < 8) L0(j + 2);
                 }
                 tc_commit(BAR(B_ACC1));
-                // ---- layer 2
-                mbar_wait(BAR(B_ACT1), ph_act1); ph_act1 ^= 1;
+                // ---- layer 2, K-chunk c as soon as the workers have converted it
                 for (int c = 0; c < 4; ++c) {
+                    mbar_wait(BAR(B_ACT1_0 + c), ph_act1);
                     const uint32_t s = cnt & 1;
                     mbar_wait(BAR(B_WFULL0 + s), (cnt >> 1) & 1); ++cnt;
                     tc_fence_after();
@@ -275,6 +284,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_query_mlp_tc(QueryParams q, c
                     }
                     tc_commit(BAR(B_WEMPTY0 + s));
                 }
+                ph_act1 ^= 1;
                 {
                     const uint32_t s = cnt & 1;
                     mbar_wait(BAR(B_WFULL0 + s), (cnt >> 1) & 1); ++cnt;
@@ -289,89 +299,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_query_mlp_tc(QueryParams q, c
                 tc_commit(BAR(B_ACC2));
             }
         }
-    } else {
+    } else if (warp < 10) {
         // ======================================================== workers (8 warps, 256 threads)
         const int q4 = warp & 3;                  // TMEM lane quarter this warp may touch
-        const int h = (warp - 2) >> 2;            // which half of the columns / features
+        const int h = (warp - 2) >> 2;            // which half of the columns
         const int r = q4 * 32 + lane;             // row of the tile = TMEM lane
         const uint32_t tl = tmem + ((uint32_t)(q4 * 32) << 16);
-        const int c0 = q.c0;
-        uint32_t ph_acc0[2] = {0, 0}, ph_a0e[2] = {0, 0}, ph_acc1 = 0, ph_acc2 = 0;
+        uint32_t ph_acc0[2] = {0, 0}, ph_a0e[2] = {0, 0}, ph_acc1 = 0, ph_acc2 = 0, ph_x0[2] = {0, 0};
         uint32_t tcount = 0;
         mbar_wait(BAR(B_W0RDY), 0);               // biases / last layer are in shared memory
         for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+            const uint32_t xb = tcount & 1;
             const int64_t pi = tile * TC_M + r;
             const bool live = pi < q.N;
-            float *xf = x0f + (tcount & 1) * (16 * TC_M);
-            // ---------------- gather: 16 features of this point -> xf[j][r]
-#pragma unroll
-            for (int i = 0; i < 8; ++i) xf[(8 * h + i) * TC_M + r] = 0.f;
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            float in_cube = 1.f;
-            if (MODE == 3) {
-                if (live)
-                    for (int j = h; j < c0; j += 2) xf[j * TC_M + r] = q.raw[(size_t)j * q.N + pi];
-            } else {
-                const float4 xyz = live ? q.xyz4[pi] : make_float4(0.f, 0.f, 0.f, 0.f);
-                in_cube = xyz.w;
-                if (live) {
-                    if (MODE == 0) {
-                        const int d = q.C / 2;
-                        const float4 *rp = (const float4 *)(q.rec + 8 * pi);
-                        const float4 r0 = rp[0], r1 = rp[1];
-                        const int fb = r1.w != 0.f ? 0 : d;          // feat_select: vis=1 front, vis=0 back
-                        const int lo_ch = h == 0 ? 0 : (d + 1) / 2, hi_ch = h == 0 ? (d + 1) / 2 : d;
-                        for (int ch = lo_ch; ch < hi_ch; ++ch)
-                            xf[ch * TC_M + r] = bilinear(q.feat + (size_t)(fb + ch) * q.H * q.W, q.H, q.W, xyz.x, xyz.y);
-                        if (h == 0) {
-                            float sdf = r0.x, cx = r0.y, cy = r0.z, cz = r0.w;
-                            if (fabsf(sdf) >= q.clip) {              // HGPIFuNet.py:299-304
-                                sdf = sdf > 0.f ? 1.f : -1.f;
-                                const long long K = *q.d_K, k3 = 3ll * (long long)q.krank[pi];
-                                cx = (float)q.signs[k3 % K];
-                                cy = (float)q.signs[(k3 + 1) % K];
-                                cz = (float)q.signs[(k3 + 2) % K];
-                            }
-                            xf[(d + 0) * TC_M + r] = sdf;
-                            xf[(d + 1) * TC_M + r] = cx;
-                            xf[(d + 2) * TC_M + r] = cy;
-                            xf[(d + 3) * TC_M + r] = cz;
-                        } else {
-                            xf[(d + 4) * TC_M + r] = r1.x;
-                            xf[(d + 5) * TC_M + r] = r1.y;
-                            xf[(d + 6) * TC_M + r] = r1.z;
-                        }
-                    } else if (MODE == 1) {
-                        for (int ch = h; ch < q.C; ch += 2)
-                            xf[ch * TC_M + r] = bilinear(q.feat + (size_t)ch * q.H * q.W, q.H, q.W, xyz.x, xyz.y);
-                        if (h == 0) xf[q.C * TC_M + r] = xyz.z;
-                    } else {
-                        if (h == 0) {
-                            for (int ch = 0; ch < q.C; ++ch)
-                                xf[ch * TC_M + r] = bilinear(q.feat + (size_t)ch * q.H * q.W, q.H, q.W, xyz.x, xyz.y);
-                        } else {
-                            const size_t vs = (size_t)q.VD * q.VD * q.VD;
-                            for (int ch = 0; ch < 7; ++ch)
-                                xf[(q.C + ch) * TC_M + r] = trilinear(q.vol + ch * vs, q.VD, xyz.x, xyz.y, xyz.z);
-                        }
-                    }
-                }
-            }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            {
-                // features 8h..8h+7 of row r -> one 16-byte K-core chunk of the hi and lo A tiles
-                uint32_t hi[4], lo[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    split2(xf[(8 * h + 2 * i) * TC_M + r], xf[(8 * h + 2 * i + 1) * TC_M + r], hi[i], lo[i]);
-                const int off = h * 2048 + (r >> 3) * 128 + (r & 7) * 16;
-                *reinterpret_cast<uint4 *>(sm + SM_X0H + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                *reinterpret_cast<uint4 *>(sm + SM_X0L + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                // the previous tile's TMEM reads of this thread are complete (wait::ld); order them
-                tc_fence_before();
-                mbar_arrive(BAR(B_X0));
-            }
+            const float *xf = x0f + xb * (16 * TC_M);
             // ---------------- layer 0 chunks -> A operand of layer 1
             for (int j = 0; j < 8; ++j) {
                 const int b = j & 1;
@@ -388,20 +329,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_query_mlp_tc(QueryParams q, c
                 tc_fence_before();
                 mbar_arrive(BAR(B_A0F0 + b));
             }
-            // ---------------- layer 1 accumulator -> A operand of layer 2
+            // ---------------- layer 1 accumulator -> A operand of layer 2, one 64-wide K-chunk at a time
             mbar_wait(BAR(B_ACC1), ph_acc1); ph_acc1 ^= 1;
             tc_fence_after();
 #pragma unroll 1
             for (int t = 0; t < 4; ++t) {
                 uint32_t acc[32], hi[16], lo[16];
-                tmem_ld32(tl + T_ACC1 + 128u * h + 32u * t, acc);
-                act_split32(acc, sb1 + 128 * h + 32 * t, hi, lo);
-                tmem_st16(tl + T_ACT1H + 64u * h + 16u * t, hi);
-                tmem_st16(tl + T_ACT1L + 64u * h + 16u * t, lo);
+                tmem_ld32(tl + T_ACC1 + 64u * t + 32u * h, acc);
+                act_split32(acc, sb1 + 64 * t + 32 * h, hi, lo);
+                tmem_st16(tl + T_ACT1H + 32u * t + 16u * h, hi);
+                tmem_st16(tl + T_ACT1L + 32u * t + 16u * h, lo);
+                tmem_st_wait();
+                tc_fence_before();
+                mbar_arrive(BAR(B_ACT1_0 + t));
             }
-            tmem_st_wait();
-            tc_fence_before();
-            mbar_arrive(BAR(B_ACT1));
             // ---------------- layer 2 accumulator -> layer 3 dot product
             mbar_wait(BAR(B_ACC2), ph_acc2); ph_acc2 ^= 1;
             tc_fence_after();
@@ -420,13 +361,97 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_query_mlp_tc(QueryParams q, c
             }
             if (h == 1) spart[r] = part;
             asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (h == 0 && live) {
-                float s = part + spart[r];
+            if (h == 0) {
+                // x0 of this tile was published by the gather warps (the MMA warp waited on the same barrier)
+                mbar_wait(BAR(B_X0R0 + xb), ph_x0[xb]);
+                if (live) {
+                    float s = part + spart[r];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) s = fmaf(sw3[128 + j], xf[j * TC_M + r], s);
-                s += sb3[0];
-                q.out[pi] = in_cube * s;
+                    for (int j = 0; j < 16; ++j) s = fmaf(sw3[128 + j], xf[j * TC_M + r], s);
+                    s += sb3[0];
+                    const float in_cube = (MODE == 3) ? 1.f : q.xyz4[pi].w;
+                    q.out[pi] = in_cube * s;
+                }
             }
+            ph_x0[xb] ^= 1;
+            // this tile's TMEM reads are complete (wait::ld) and x0 buffer xb is no longer needed
+            tc_fence_before();
+            mbar_arrive(BAR(B_X0F0 + xb));
+        }
+    } else {
+        // ======================================================== gather warps (4 warps, one row per thread):
+        // features of tile i+1 are produced while tile i is in the tensor pipe
+        const int r = (warp - 10) * 32 + lane;
+        const int c0 = q.c0;
+        uint32_t ph_free[2] = {0, 0};
+        uint32_t tcount = 0;
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+            const uint32_t xb = tcount & 1;
+            const int64_t pi = tile * TC_M + r;
+            const bool live = pi < q.N;
+            float f[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = 0.f;
+            if (live) {
+                if (MODE == 3) {
+                    for (int j = 0; j < c0; ++j) f[j] = q.raw[(size_t)j * q.N + pi];
+                } else {
+                    const float4 xyz = q.xyz4[pi];
+                    if (MODE == 0) {
+                        const int d = q.C / 2;
+                        const float4 *rp = (const float4 *)(q.rec + 8 * pi);
+                        const float4 r0 = rp[0], r1 = rp[1];
+                        const int fb = r1.w != 0.f ? 0 : d;          // feat_select: vis=1 front, vis=0 back
+                        float sdf = r0.x, cx = r0.y, cy = r0.z, cz = r0.w;
+                        if (fabsf(sdf) >= q.clip) {                  // HGPIFuNet.py:299-304
+                            sdf = sdf > 0.f ? 1.f : -1.f;
+                            const long long K = *q.d_K, k3 = 3ll * (long long)q.krank[pi];
+                            cx = (float)q.signs[k3 % K];
+                            cy = (float)q.signs[(k3 + 1) % K];
+                            cz = (float)q.signs[(k3 + 2) % K];
+                        }
+                        if (d == 6) {
+#pragma unroll
+                            for (int ch = 0; ch < 6; ++ch)
+                                f[ch] = bilinear(q.feat + (size_t)(fb + ch) * q.H * q.W, q.H, q.W, xyz.x, xyz.y);
+                            f[6] = sdf; f[7] = cx; f[8] = cy; f[9] = cz; f[10] = r1.x; f[11] = r1.y; f[12] = r1.z;
+                        } else {
+#pragma unroll
+                            for (int ch = 0; ch < 3; ++ch)
+                                f[ch] = bilinear(q.feat + (size_t)(fb + ch) * q.H * q.W, q.H, q.W, xyz.x, xyz.y);
+                            f[3] = sdf; f[4] = cx; f[5] = cy; f[6] = cz; f[7] = r1.x; f[8] = r1.y; f[9] = r1.z;
+                        }
+                    } else if (MODE == 1) {
+#pragma unroll
+                        for (int ch = 0; ch < 12; ++ch)
+                            f[ch] = bilinear(q.feat + (size_t)ch * q.H * q.W, q.H, q.W, xyz.x, xyz.y);
+                        f[12] = xyz.z;
+                    } else {
+                        const size_t vs = (size_t)q.VD * q.VD * q.VD;
+#pragma unroll
+                        for (int ch = 0; ch < 6; ++ch)
+                            f[ch] = bilinear(q.feat + (size_t)ch * q.H * q.W, q.H, q.W, xyz.x, xyz.y);
+#pragma unroll
+                        for (int ch = 0; ch < 7; ++ch)
+                            f[6 + ch] = trilinear(q.vol + ch * vs, q.VD, xyz.x, xyz.y, xyz.z);
+                    }
+                }
+            }
+            // buffer xb free? (workers finished the tile that used it, which implies its MMAs completed)
+            mbar_wait(BAR(B_X0F0 + xb), ph_free[xb] ^ 1); ph_free[xb] ^= 1;
+            float *xf = x0f + xb * (16 * TC_M);
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) xf[j * TC_M + r] = f[j];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) split2(f[2 * i], f[2 * i + 1], hi[i], lo[i]);
+            const int off = (int)xb * 4096 + (r >> 3) * 128 + (r & 7) * 16;
+            *reinterpret_cast<uint4 *>(sm + SM_X0H + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4 *>(sm + SM_X0H + off + 2048) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+            *reinterpret_cast<uint4 *>(sm + SM_X0L + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            *reinterpret_cast<uint4 *>(sm + SM_X0L + off + 2048) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(BAR(B_X0R0 + xb));
         }
     }
 

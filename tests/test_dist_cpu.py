@@ -1,0 +1,46 @@
+"""N>1 plumbing on CPU: world_size-2 gloo (the GPU path uses the same functions over NCCL)."""
+import os
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from icon_b200 import dist as D
+
+
+def test_shard_images_covers_every_image_once():
+    for n, w in [(8, 1), (8, 2), (32, 8), (64, 8), (5, 4), (3, 8)]:
+        got = [i for r in range(w) for i in D.shard_images(n, r, w)]
+        assert got == list(range(n))
+        sizes = [len(D.shard_images(n, r, w)) for r in range(w)]
+        assert max(sizes) - min(s for s in sizes if s or True) <= (n + w - 1) // w
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        mine = D.shard_images(5, rank, world)
+        ms = D.max_over_ranks([10.0 + rank, 3.0 - rank], torch.device("cpu"))
+        hdrs = D.gather_headers([float(rank), float(len(mine)), float(sum(mine))], torch.device("cpu"))
+        dist.barrier()
+        q.put((rank, mine, ms, hdrs))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2_max_and_gather():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (r0, m0, ms0, h0), (r1, m1, ms1, h1) = res
+    assert m0 == [0, 1, 2] and m1 == [3, 4]
+    assert ms0 == ms1 == [11.0, 3.0]                      # max over ranks, element-wise
+    assert h0 == h1 == [[0.0, 3.0, 3.0], [1.0, 2.0, 7.0]]  # every rank sees every header, in rank order
