@@ -9,8 +9,75 @@ from ._C import check, lib
 from .ops import _need_cuda, _p, _stream
 
 
+_IMPL = "auto"        # "auto": tcgen05 kernel when Cin % 64 == 0, FP32 kernel otherwise; "fp32": always FP32
+_PACK_CACHE = {}
+NUM_SMS = 148
+
+
+def set_conv_impl(name):
+    global _IMPL
+    assert name in ("auto", "fp32")
+    _IMPL = name
+
+
 def _c(t):
     return t.detach().float().contiguous()
+
+
+def _pack_tc(w, transposed, n_tile):
+    """torch conv weight -> device blob of K-major SWIZZLE_128B fp16 hi/lo tiles (include/icon_b200.h)."""
+    key = (w.data_ptr(), w._version, tuple(w.shape), transposed, n_tile, str(w.device))
+    hit = _PACK_CACHE.get(key)
+    if hit is not None:
+        return hit
+    wd = w.detach().float()
+    if transposed:                                   # [Cin, Cout, KH, KW] -> [Cout, taps*Cin]
+        w2 = wd.permute(1, 2, 3, 0).reshape(wd.shape[1], -1)
+    else:                                            # [Cout, Cin, KH, KW] -> [Cout, taps*Cin], k = tap*Cin + ci
+        w2 = wd.permute(0, 2, 3, 1).reshape(wd.shape[0], -1)
+    cout, K = w2.shape
+    ntl = (cout + n_tile - 1) // n_tile
+    if ntl * n_tile != cout:
+        w2 = torch.cat([w2, torch.zeros(ntl * n_tile - cout, K, device=w2.device)], 0)
+    hi = w2.half()
+    lo = (w2 - hi.float()).half()
+    nch = K // 64
+    r = torch.arange(n_tile, device=w2.device)
+    cpos = torch.arange(8, device=w2.device)
+    src_chunk = (cpos[None, :] ^ (r % 8)[:, None])                       # [r, c'] -> source 16-byte chunk
+    index = src_chunk[None, :, None, :, None].expand(ntl, n_tile, nch, 8, 8)
+
+    def tiles(m):
+        t = m.view(ntl, n_tile, nch, 8, 8)                               # [tile, row, chunk, c16, elem]
+        return t.gather(3, index).permute(0, 2, 1, 3, 4)                 # -> [tile, chunk, row, c16', elem]
+
+    blob = torch.stack([tiles(hi), tiles(lo)], dim=2).contiguous().view(torch.uint8).reshape(-1)
+    if len(_PACK_CACHE) > 256:
+        _PACK_CACHE.clear()
+    _PACK_CACHE[key] = blob
+    return blob
+
+
+def _tc_plan(npix, cout, chunks):
+    n_tile = 256 if cout >= 256 else (128 if cout >= 128 else 64)
+    mt = (npix + 127) // 128
+    while n_tile > 64 and mt * ((cout + n_tile - 1) // n_tile) < NUM_SMS:
+        n_tile //= 2
+    items = mt * ((cout + n_tile - 1) // n_tile)
+    splits = 1
+    if items < NUM_SMS:
+        splits = max(1, min(8, NUM_SMS // items, chunks))
+    return n_tile, splits
+
+
+def _conv_tc(x, w, b, r, y, N, Cin, H, W, Cout, KH, KW, stride, pad, out_pad, reflect, transposed, act):
+    OH, OW = y.shape[2], y.shape[3]
+    n_tile, splits = _tc_plan(N * OH * OW, Cout, KH * KW * (Cin // 64))
+    blob = _pack_tc(w, bool(transposed), n_tile)
+    nbytes = lib.icon_conv2d_tc_workspace_bytes(N, Cout, OH, OW, splits)
+    ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=x.device)
+    check(lib.icon_conv2d_tc(_p(x), _p(blob), _p(b), _p(r), _p(y), N, Cin, H, W, Cout, KH, KW, stride, pad, out_pad,
+                             reflect, transposed, act, n_tile, splits, _p(ws), nbytes, _stream()), "icon_conv2d_tc")
 
 
 def conv2d(x, conv, reflect=0, tanh=False, relu=False, residual=None):
@@ -29,8 +96,12 @@ def conv2d(x, conv, reflect=0, tanh=False, relu=False, residual=None):
     y = torch.empty(N, Cout, OH, OW, dtype=torch.float32, device=x.device)
     b = _c(conv.bias) if conv.bias is not None else None
     r = _c(residual) if residual is not None else None
+    act = 2 if tanh else (1 if relu else 0)
+    if _IMPL == "auto" and Cin % 64 == 0:
+        _conv_tc(x, conv.weight, b, r, y, N, Cin, H, W, Cout, KH, KW, stride, pad, 0, 1 if reflect else 0, 0, act)
+        return y
     check(lib.icon_conv2d(_p(x), _p(w), _p(b), _p(r), _p(y), N, Cin, H, W, Cout, KH, KW, stride, pad, 0,
-                          1 if reflect else 0, 0, 2 if tanh else (1 if relu else 0), _stream()), "icon_conv2d")
+                          1 if reflect else 0, 0, act, _stream()), "icon_conv2d")
     return y
 
 
@@ -46,6 +117,9 @@ def conv_transpose2d(x, conv):
     OW = (W - 1) * s - 2 * p + KW + op
     y = torch.empty(N, Cout, OH, OW, dtype=torch.float32, device=x.device)
     b = _c(conv.bias) if conv.bias is not None else None
+    if _IMPL == "auto" and Cin % 64 == 0:
+        _conv_tc(x, conv.weight, b, None, y, N, Cin, H, W, Cout, KH, KW, s, p, op, 0, 1, 0)
+        return y
     check(lib.icon_conv2d(_p(x), _p(w), _p(b), None, _p(y), N, Cin, H, W, Cout, KH, KW, s, p, op, 0, 1, 0, _stream()),
           "icon_conv2d(transposed)")
     return y

@@ -183,6 +183,14 @@ int icon_mc_emit(const float *occ, int R, float iso, int padded, const void *ws,
 int icon_conv2d(const float *x, const float *w, const float *bias, const float *res, float *y, int N, int Cin,
                 int H, int W, int Cout, int KH, int KW, int stride, int pad, int out_pad, int reflect,
                 int transposed, int act, icon_stream_t stream);
+/* Tensor-core (tcgen05, fp16 hi/lo x3, fp32-class accuracy) variant for Cin % 64 == 0; same semantics.
+ * wt_packed: per output-channel tile (n_tile rows, zero padded) and per 64-wide K-chunk (k = tap*Cin + ci) a
+ * K-major SWIZZLE_128B tile of the fp16 hi parts followed by one of the lo parts (icon_b200/conv_ops.py packs
+ * it).  splits > 1 = split-K over the chunks, partial sums in `ws` (icon_conv2d_tc_workspace_bytes). */
+size_t icon_conv2d_tc_workspace_bytes(int N, int Cout, int OH, int OW, int splits);
+int icon_conv2d_tc(const float *x, const void *wt_packed, const float *bias, const float *res, float *y, int N,
+                   int Cin, int H, int W, int Cout, int KH, int KW, int stride, int pad, int out_pad, int reflect,
+                   int transposed, int act, int n_tile, int splits, void *ws, size_t ws_bytes, icon_stream_t stream);
 int icon_group_norm(const float *x, const float *gamma, const float *beta, const float *res, float *y, int N,
                     int C, int HW, int groups, float eps, int relu, icon_stream_t stream);
 /* F.avg_pool2d(x, 2, stride=2); planes = N*C */

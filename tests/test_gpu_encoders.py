@@ -35,23 +35,48 @@ def test_conv2d_matches_torch(cin, cout, k, s, p, reflect, hw):
         ref = conv(F.pad(x, (reflect,) * 4, mode="reflect") if reflect else x)
         res = torch.randn(ref.shape, generator=_g(7))
         ref_r = torch.tanh(ref + res)
-    y = C.conv2d(x.to(dev), conv.to(dev), reflect=reflect)
-    assert y.shape == ref.shape
-    assert (y.cpu() - ref).abs().max() <= 2e-5 * max(1.0, ref.abs().max().item())
-    y2 = C.conv2d(x.to(dev), conv, reflect=reflect, tanh=True, residual=res.to(dev))
-    assert (y2.cpu() - ref_r).abs().max() <= 2e-5
+    for impl in ("auto", "fp32"):                 # auto = tcgen05 kernel when Cin % 64 == 0
+        C.set_conv_impl(impl)
+        try:
+            y = C.conv2d(x.to(dev), conv.to(dev), reflect=reflect)
+            assert y.shape == ref.shape
+            assert (y.cpu() - ref).abs().max() <= 5e-5 * max(1.0, ref.abs().max().item()), impl
+            y2 = C.conv2d(x.to(dev), conv, reflect=reflect, tanh=True, residual=res.to(dev))
+            assert (y2.cpu() - ref_r).abs().max() <= 5e-5, impl
+        finally:
+            C.set_conv_impl("auto")
+
+
+@pytest.mark.parametrize("cin,cout,k,s,p,reflect,hw,relu", [
+    (256, 256, 3, 1, 1, 0, 16, True),        # small spatial -> split-K
+    (1024, 1024, 3, 1, 1, 1, 8, False),      # ResnetBlock shape (reflect), split-K over 144 chunks
+    (128, 96, 3, 2, 1, 0, 40, False),        # Cout not a multiple of the tile, stride 2
+    (64, 32, 1, 1, 0, 0, 64, True)])
+def test_conv2d_tensor_core_shapes(cin, cout, k, s, p, reflect, hw, relu):
+    dev = _cuda()
+    from icon_b200 import conv_ops as C
+    conv = nn.Conv2d(cin, cout, k, stride=s, padding=0 if reflect else p)
+    x = torch.randn(1, cin, hw, hw, generator=_g(cin + k))
+    with torch.no_grad():
+        ref = conv(F.pad(x, (reflect,) * 4, mode="reflect") if reflect else x)
+        if relu:
+            ref = F.relu(ref)
+    y = C.conv2d(x.to(dev), conv.to(dev), reflect=reflect, relu=relu)
+    err = (y.cpu() - ref).abs().max().item()
+    assert err <= 5e-5 * max(1.0, ref.abs().max().item()), err
 
 
 def test_conv_transpose2d_matches_torch():
     dev = _cuda()
     from icon_b200 import conv_ops as C
-    ct = nn.ConvTranspose2d(48, 24, 3, stride=2, padding=1, output_padding=1)
-    x = torch.randn(2, 48, 17, 19, generator=_g(1))
-    with torch.no_grad():
-        ref = ct(x)
-    y = C.conv_transpose2d(x.to(dev), ct.to(dev))
-    assert y.shape == ref.shape
-    assert (y.cpu() - ref).abs().max() <= 2e-5
+    for cin, cout in ((48, 24), (128, 64)):          # FP32 kernel / tcgen05 kernel
+        ct = nn.ConvTranspose2d(cin, cout, 3, stride=2, padding=1, output_padding=1)
+        x = torch.randn(2, cin, 17, 19, generator=_g(1))
+        with torch.no_grad():
+            ref = ct(x)
+        y = C.conv_transpose2d(x.to(dev), ct.to(dev))
+        assert y.shape == ref.shape
+        assert (y.cpu() - ref).abs().max() <= 5e-5, (cin, cout)
 
 
 def test_norms_pool_bicubic_joins_match_torch():
