@@ -59,14 +59,13 @@ def _pack_tc(w, transposed, n_tile):
 
 
 def _tc_plan(npix, cout, chunks):
-    n_tile = 256 if cout >= 256 else (128 if cout >= 128 else 64)
-    mt = (npix + 127) // 128
-    while n_tile > 64 and mt * ((cout + n_tile - 1) // n_tile) < NUM_SMS:
-        n_tile //= 2
-    items = mt * ((cout + n_tile - 1) // n_tile)
+    """Widest channel tile the layer allows (N=256 MMAs run at 93 % of the tensor rate, N<=128 pay a flat
+    ~93 cycles each: tools/umma_rate.cu); fill the SMs with split-K rather than with narrower tiles."""
+    n_tile = 256 if cout > 128 else (128 if cout > 64 else 64)
+    items = ((npix + 127) // 128) * ((cout + n_tile - 1) // n_tile)
     splits = 1
     if items < NUM_SMS:
-        splits = max(1, min(8, NUM_SMS // items, chunks))
+        splits = max(1, min(16, NUM_SMS // items, chunks))
     return n_tile, splits
 
 
