@@ -221,6 +221,8 @@ class HGPIFuNet(BasePIFuNet):
             self.smpl_feat_dict = {k: in_tensor_dict[k] for k in self.pamir_keys if k in in_tensor_dict}
             if "vol_feat" in in_tensor_dict:      # pre-encoded volume feature
                 self._vol_feat = in_tensor_dict["vol_feat"]
+            elif "vol" in in_tensor_dict:         # semantic volume [1,3,128,128,128] -> VolumeEncoder, once per subject
+                self._vol_feat = self.ve(in_tensor_dict["vol"], intermediate_output=False)[-1]
         features_out = [features_G[-1]] if not self.training else features_G
         if return_inter:
             return features_out, in_filter
@@ -257,8 +259,9 @@ class HGPIFuNet(BasePIFuNet):
         if self.prior_type == "pamir":
             vol = self._vol_feat
             if vol is None:
-                raise NotImplementedError("pamir prior: pass a pre-encoded in_tensor_dict['vol_feat'] "
-                                          "(voxelisation kernel: DESIGN.md 'next')")
+                raise NotImplementedError("pamir prior: pass in_tensor_dict['vol'] (semantic volume) or a pre-encoded "
+                                          "in_tensor_dict['vol_feat'] to filter(); the voxelisation kernel itself "
+                                          "(voxelize_cuda, source absent) is not restated (DESIGN.md section 7)")
         with torch.no_grad():
             for im_feat in features:
                 preds = ops.query(self.prior_type, points, calibs, im_feat, regressor.packed(),

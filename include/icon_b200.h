@@ -193,6 +193,12 @@ int icon_conv2d_tc(const float *x, const void *wt_packed, const float *bias, con
                    int transposed, int act, int n_tile, int splits, void *ws, size_t ws_bytes, icon_stream_t stream);
 int icon_group_norm(const float *x, const float *gamma, const float *beta, const float *res, float *y, int N,
                     int C, int HW, int groups, float eps, int relu, icon_stream_t stream);
+/* nn.Conv3d (B = 1, Cout <= 8, cubic kernel / stride / padding / dilation) followed by eval-mode BatchNorm3d
+ * folded into per-channel (scale, shift), optional residual add and ReLU: the layers of PaMIR's VolumeEncoder
+ * (lib/net/VE.py:96-183).  x [Cin,D,H,W], w [Cout,Cin,k,k,k], y [Cout,OD,OH,OW]. */
+int icon_conv3d(const float *x, const float *w, const float *scale, const float *shift, const float *res, float *y,
+                int Cin, int Cout, int D, int H, int W, int k, int stride, int pad, int dil, int relu,
+                icon_stream_t stream);
 /* F.avg_pool2d(x, 2, stride=2); planes = N*C */
 int icon_avg_pool2(const float *x, float *y, int64_t planes, int H, int W, icon_stream_t stream);
 /* y = add + F.interpolate(x, scale_factor=2, mode="bicubic", align_corners=True) (HGFilters.py:70-76) */

@@ -144,6 +144,11 @@ def main():
     with torch.no_grad():
         y6 = gg(x6)
     enc["gg_x"], enc["gg_y"] = x6.numpy(), y6.numpy()
+    ve.load_state_dict(seeded_state_dict(ve, 23)); ve.eval()
+    xv = torch.rand(1, 3, 32, 32, 32, generator=g)
+    with torch.no_grad():
+        yv = ve(xv, intermediate_output=False)
+    enc["ve_x"], enc["ve_y"] = xv.numpy(), yv[-1].numpy()
     np.savez_compressed(os.path.join(HERE, "encoders.npz"), **enc)
     print("golden fixtures written to", HERE)
 

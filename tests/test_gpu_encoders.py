@@ -140,6 +140,18 @@ def test_global_generator_matches_reference_module(golden_dir):
     assert err <= 2e-4, err
 
 
+def test_volume_encoder_matches_reference_module(golden_dir):
+    dev = _cuda()
+    from icon_b200.encoders import VolumeEncoder
+    g = np.load(os.path.join(golden_dir, "encoders.npz"))
+    ve = VolumeEncoder(3, 7, 2)
+    ve.load_state_dict(S.seeded_like(ve.state_dict(), 23))
+    ve = ve.to(dev).eval()
+    y = ve(torch.from_numpy(g["ve_x"]).to(dev), intermediate_output=False)
+    assert len(y) == 1 and tuple(y[0].shape) == tuple(g["ve_y"].shape)
+    assert np.abs(y[0].cpu().numpy() - g["ve_y"]).max() <= 1e-4
+
+
 def test_filter_icon_filter_config_shapes_and_timing():
     """HGPIFuNet.filter on the BASELINE config (icon-filter, 512x512): NormalNet + 2 x HGFilter."""
     dev = _cuda()

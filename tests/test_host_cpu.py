@@ -140,3 +140,16 @@ def test_oracle_marching_cubes_is_watertight_and_matches_analytic_sphere():
     # consistent orientation: signed volume is positive or negative for ALL faces summed, and matches 4/3 pi r^3
     vol = np.einsum("ij,ij->i", p[f[:, 0]], np.cross(p[f[:, 1]], p[f[:, 2]])).sum() / 6.0
     assert abs(abs(vol) - 4.0 / 3.0 * np.pi * 0.6 ** 3) < 2e-2
+
+
+def test_display_preview_runs_on_cpu_tensor():
+    """R14 (training preview): plain torch restatement of seg3d_lossless.py:498-581, shape/dtype contract."""
+    import numpy as np
+    from icon_b200.engine import Seg3dLossless
+    eng = Seg3dLossless(None, [[-1.0, 1, -1]], [[1.0, -1, 1]], resolutions=[17, 33], align_corners=True, faster=True)
+    a = torch.linspace(-1, 1, 33)
+    z, y, x = torch.meshgrid(a, a, a, indexing="ij")
+    occ = 0.5 + (0.6 - torch.sqrt(x * x + y * y + z * z))
+    img = eng.display(occ)
+    assert img.shape == (33, 4 * 33, 3) and img.dtype == np.uint8
+    assert (img != 255).any()
