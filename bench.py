@@ -253,14 +253,11 @@ def main():
             stage[i] += buf[i] / args.steps
     _C.lib.icon_profile_enable(0)
 
-    if world > 1:
-        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e = float(t[0]), float(t[1])
-        # final gather (the only collective on the path): per-image header to rank 0
-        hdr = torch.tensor([float(rank), float(N), checksum], device=dev, dtype=torch.float64)
-        allh = [torch.empty_like(hdr) for _ in range(world)]
-        dist.all_gather(allh, hdr)
+    from icon_b200 import dist as D
+    ms, ms_e2e = D.max_over_ranks([ms, ms_e2e], dev)             # device-timed, max over ranks
+    # final gather (the only collective on the path): one header per image to every rank
+    headers = D.gather_headers([float(rank), float(N), checksum], dev)
+    assert len(headers) == world
 
     if rank == 0:
         peaks = _peaks()
@@ -293,7 +290,7 @@ def main():
                          "note": "achieved = algorithmic MLP FLOPs (344,602/pt x points) / kernel time; the kernel "
                                  "executes 3 fp16 MMAs per algorithmic one to hold 1e-4 (executed_*); traffic = "
                                  "dram read+write bytes per launch from profiles/ (ncu --set full)"},
-            "checksum": checksum,
+            "checksum": checksum, "image_headers": headers,
         }
         if not args.no_cpu_baseline and world == 1:
             r, dt, threads = cpu_port_rate(sd, smpl_cpu, feat_cpu, 262144)
