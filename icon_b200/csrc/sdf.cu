@@ -77,7 +77,7 @@ __device__ __forceinline__ void emit_record(V3 p, int bi, float best, int hits, 
 constexpr int SW_T = 128;               // 4 warps per block, one warp = 32 Morton-adjacent points
 constexpr int NBIN_AX = 128;            // Morton bins per axis over [-1,1]^3 (+1 overflow bin)
 constexpr int NBIN = NBIN_AX * NBIN_AX * NBIN_AX;
-constexpr int FR_CAP = 2048;            // frontier / leaf list capacity per warp
+constexpr int FR_CAP = 1536;            // frontier / leaf list capacity per warp
 
 __device__ __forceinline__ float box_dist2(V3 p, float4 lo, float4 hi) {
     float dx = fmaxf(fmaxf(lo.x - p.x, p.x - hi.x), 0.f);
@@ -158,7 +158,8 @@ __device__ unsigned long long g_stats[8];   // warps, overflow warps, sum leaves
 
 struct WarpSmem {
     unsigned short fr[2][FR_CAP];      // node / leaf ids (leaf count <= 65535 is checked by the host)
-    float4 sph[32];                    // bounding spheres of the 32 faces of the current chunk
+    float4 sph[32];                    // bounding spheres of the surviving faces of the current chunk (compacted)
+    float4 tri[32][3];                 // their (a, ab, ac) records
     int kk[32];                        // their sorted positions
 };
 
@@ -186,6 +187,9 @@ __global__ void __launch_bounds__(SW_T) k_sdf_warp(const float4 *__restrict__ xy
     const V3 c = mk3(0.5f * (warp_min(p.x) + warp_max(p.x)), 0.5f * (warp_min(p.y) + warp_max(p.y)),
                      0.5f * (warp_min(p.z) + warp_max(p.z)));
     const float rw = warp_max(sqrtf(dot3(sub3(p, c), sub3(p, c)))) * 1.00001f + 1e-6f;
+    // the warp's bounding box (tighter than the sphere for the flat 4x4x2 blocks of a lattice)
+    const float4 wlo = make_float4(warp_min(p.x) - 1e-6f, warp_min(p.y) - 1e-6f, warp_min(p.z) - 1e-6f, 0.f);
+    const float4 whi = make_float4(warp_max(p.x) + 1e-6f, warp_max(p.y) + 1e-6f, warp_max(p.z) + 1e-6f, 0.f);
 
     float best = FLT_MAX;
     int bi = 0x7fffffff;
@@ -217,8 +221,8 @@ __global__ void __launch_bounds__(SW_T) k_sdf_warp(const float4 *__restrict__ xy
         for (int k = 4 * node; k < min(4 * node + 4, m.F); ++k) try_face(k);
     }
     const float ubw = warp_max(sqrtf(best));                  // every lane's nearest is within ubw
-    float lim = (ubw + rw) * 1.00001f + 1e-6f;                // bound on d(warp centre, any lane's nearest face)
-    float lim2 = lim * lim;
+    float ubw2 = ubw;                                         // bound on d(lane, its nearest face), all lanes
+    float ub2 = (ubw2 * 1.00001f + 1e-6f) * (ubw2 * 1.00001f + 1e-6f);
 
     // ---- phase B: breadth-first cull of the tree, 32 child boxes per step.  The bound also
     //      tightens on the way down: some face lies within the nearest far-corner distance of c,
@@ -240,7 +244,11 @@ __global__ void __launch_bounds__(SW_T) k_sdf_warp(const float4 *__restrict__ xy
                 ch = 4 * (int)S.fr[cur][slot] + (lane & 3);
                 if (ch < ccnt) {
                     const float4 lo = __ldg(nodes + 2 * (size_t)ch), hi = __ldg(nodes + 2 * (size_t)ch + 1);
-                    pass = box_dist2(c, lo, hi) <= lim2;
+                    // distance between the node's box and the warp's box bounds every lane's distance to the node
+                    const float gx = fmaxf(fmaxf(lo.x - whi.x, wlo.x - hi.x), 0.f);
+                    const float gy = fmaxf(fmaxf(lo.y - whi.y, wlo.y - hi.y), 0.f);
+                    const float gz = fmaxf(fmaxf(lo.z - whi.z, wlo.z - hi.z), 0.f);
+                    pass = fmaf(gz, gz, fmaf(gy, gy, gx * gx)) <= ub2;
                     far2 = fminf(far2, box_far2(c, lo, hi));
                 }
             }
@@ -252,29 +260,32 @@ __global__ void __launch_bounds__(SW_T) k_sdf_warp(const float4 *__restrict__ xy
         if (nn > FR_CAP) overflow = true;
         n = nn;
         cur ^= 1;
-        const float l2 = (sqrtf(warp_min(far2)) + 2.f * rw) * 1.00001f + 1e-6f;
-        if (l2 < lim) { lim = l2; lim2 = l2 * l2; }
+        // some face lies within the nearest far-corner distance of c -> within that + rw of every lane
+        const float l2 = sqrtf(warp_min(far2)) + rw;
+        if (l2 < ubw2) { ubw2 = l2; ub2 = (ubw2 * 1.00001f + 1e-6f) * (ubw2 * 1.00001f + 1e-6f); }
         __syncwarp();
     }
     STAT(0, 1); STAT(1, overflow ? 1 : 0); STAT(2, n);
-    // ---- phases C+D: 32 faces (8 leaves) at a time: cull by bounding sphere against the warp bound,
-    //      then every lane tests the survivors against its own best through two cheap lower bounds
-    //      (bounding sphere, then the support-function bound d >= |w| - max_k u.(v_k - c_f), u = w/|w|,
-    //      w = p - c_f, which is nearly exact for faces seen head-on) before the exact distance.
+    // ---- phases C+D: 32 faces (8 leaves) at a time: cull by bounding sphere against the warp's box and bound,
+    //      stage the survivors (sphere + triangle) compacted in shared memory, then every lane tests them against
+    //      its own best through two cheap lower bounds (bounding sphere, then the support-function bound
+    //      d >= |w| - max_k u.(v_k - c_f), u = w/|w|, w = p - c_f, nearly exact for faces seen head-on) before
+    //      the exact distance.
     {
         float sbA = best * rsqrtf(best) * 1.00001f + 1e-6f;    // ~sqrt(best), inflated; bounds only
-        auto lane_test = [&](int k, float4 s) {
+        const float ubA = ubw2 * 1.00001f + 1e-6f;
+        auto lane_test = [&](int k, float4 s, float4 r0, float4 r1, float4 r2) {
             const float dx = p.x - s.x, dy = p.y - s.y, dz = p.z - s.z;
             const float dd = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
             const float l = sbA + s.w;
             if (dd > l * l) return;                            // sphere bound beats this lane's best
-            const Tri tr = load_tri(m.tri_s + 3 * (size_t)k);
-            const float S1 = fmaf(dz, tr.ab.z, fmaf(dy, tr.ab.y, dx * tr.ab.x));
-            const float T1 = fmaf(dz, tr.ac.z, fmaf(dy, tr.ac.y, dx * tr.ac.x));
+            const V3 ab = mk3(r0.w, r1.x, r1.y), ac = mk3(r1.z, r1.w, r2.x);
+            const float S1 = fmaf(dz, ab.z, fmaf(dy, ab.y, dx * ab.x));
+            const float T1 = fmaf(dz, ac.z, fmaf(dy, ac.y, dx * ac.x));
             const float M = fmaxf(fmaxf(-(S1 + T1), fmaf(2.f, S1, -T1)), fmaf(2.f, T1, -S1)) * (1.f / 3.f);
             const float g = dd - M - 1e-7f;                    // |w|^2 - |w| h(u)
             if (g > 0.f && g * g > best * dd * 1.0001f) return;   // support bound beats this lane's best
-            const float d = tri_sqdist(p, tr.a, tr.ab, tr.ac);
+            const float d = tri_sqdist(p, mk3(r0.x, r0.y, r0.z), ab, ac);
             const int f = __ldg(m.order + k);
             if (d < best || (d == best && f < bi)) {
                 best = d; bi = f;
@@ -292,24 +303,29 @@ __global__ void __launch_bounds__(SW_T) k_sdf_warp(const float4 *__restrict__ xy
                     k = 4 * (int)S.fr[cur][slot] + (lane & 3);
                     if (k < m.F) {
                         s = __ldg(m.sph_s + k);
-                        const float dx = c.x - s.x, dy = c.y - s.y, dz = c.z - s.z;
-                        const float l2 = lim + s.w;
-                        pass = fmaf(dz, dz, fmaf(dy, dy, dx * dx)) <= l2 * l2;
+                        const float l2 = ubA + s.w;            // sphere vs the warp's box: some lane may be that close
+                        pass = box_dist2(mk3(s.x, s.y, s.z), wlo, whi) <= l2 * l2;
                     }
                 }
-                S.sph[lane] = s;
-                S.kk[lane] = k;
-                unsigned mask = __ballot_sync(0xffffffffu, pass);
-                STAT(3, __popc(mask));
-                while (mask) {
-                    const int src = __ffs(mask) - 1;
-                    mask &= mask - 1;
-                    lane_test(S.kk[src], S.sph[src]);
+                const unsigned mask = __ballot_sync(0xffffffffu, pass);
+                const int cnt = __popc(mask);
+                STAT(3, cnt);
+                if (pass) {
+                    const int at = __popc(mask & ((1u << lane) - 1u));
+                    const float4 *tp = m.tri_s + 3 * (size_t)k;
+                    S.sph[at] = s;
+                    S.kk[at] = k;
+                    S.tri[at][0] = __ldg(tp); S.tri[at][1] = __ldg(tp + 1); S.tri[at][2] = __ldg(tp + 2);
                 }
+                __syncwarp();
+                for (int j = 0; j < cnt; ++j) lane_test(S.kk[j], S.sph[j], S.tri[j][0], S.tri[j][1], S.tri[j][2]);
                 __syncwarp();
             }
         } else {
-            for (int k = 0; k < m.F; ++k) lane_test(k, __ldg(m.sph_s + k));
+            for (int k = 0; k < m.F; ++k) {
+                const float4 *tp = m.tri_s + 3 * (size_t)k;
+                lane_test(k, __ldg(m.sph_s + k), __ldg(tp), __ldg(tp + 1), __ldg(tp + 2));
+            }
         }
     }
     // ---- +x ray parity
