@@ -46,7 +46,7 @@ _SIGS = {
     "icon_conv2d_tc_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "icon_conv2d_tc": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _sz,
                            _vp]),
-    "icon_group_norm": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp]),
+    "icon_group_norm": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp, _vp]),
     "icon_conv3d": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "icon_avg_pool2": (_i, [_vp, _vp, _i64, _i, _i, _vp]),
     "icon_bicubic_up2_add": (_i, [_vp, _vp, _vp, _i64, _i, _i, _vp]),

@@ -129,8 +129,9 @@ def group_norm(x, gn, relu=False):
     x = _c(x)
     N, C, H, W = x.shape
     y = torch.empty_like(x)
+    st = torch.empty(2 * N * gn.num_groups, dtype=torch.float64, device=x.device)
     check(lib.icon_group_norm(_p(x), _p(_c(gn.weight)), _p(_c(gn.bias)), None, _p(y), N, C, H * W, gn.num_groups,
-                              float(gn.eps), 1 if relu else 0, _stream()), "icon_group_norm")
+                              float(gn.eps), 1 if relu else 0, _p(st), _stream()), "icon_group_norm")
     return y
 
 
@@ -140,8 +141,9 @@ def instance_norm(x, relu=False, residual=None, eps=1e-5):
     N, C, H, W = x.shape
     y = torch.empty_like(x)
     r = _c(residual) if residual is not None else None
-    check(lib.icon_group_norm(_p(x), None, None, _p(r), _p(y), N, C, H * W, C, float(eps), 1 if relu else 0, _stream()),
-          "icon_group_norm(instance)")
+    st = torch.empty(2 * N * C, dtype=torch.float64, device=x.device)
+    check(lib.icon_group_norm(_p(x), None, None, _p(r), _p(y), N, C, H * W, C, float(eps), 1 if relu else 0, _p(st),
+                              _stream()), "icon_group_norm(instance)")
     return y
 
 

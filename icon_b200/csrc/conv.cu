@@ -183,6 +183,88 @@ __global__ void __launch_bounds__(512) k_group_norm(const float *__restrict__ x,
     }
 }
 
+// small groups (InstanceNorm at 32x32 .. 64x64): one WARP per (sample, group), values kept in registers,
+// shuffle reductions only.  cnt <= 32 * NV.
+template <int NV>
+__global__ void __launch_bounds__(256) k_group_norm_warp(const float *__restrict__ x, const float *__restrict__ gamma,
+                                                         const float *__restrict__ beta, const float *__restrict__ res,
+                                                         float *__restrict__ y, int C, int HW, int groups, float eps,
+                                                         int relu, int ngroups_total) {
+    const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (gw >= ngroups_total) return;
+    const int n = gw / groups, g = gw % groups, cpg = C / groups;
+    const size_t base = ((size_t)n * C + (size_t)g * cpg) * HW;
+    const int cnt = cpg * HW;
+    float v[NV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int idx = lane + 32 * i;
+        v[i] = idx < cnt ? x[base + idx] : 0.f;
+        s += v[i];
+    }
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / (float)cnt;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const float d = (lane + 32 * i < cnt) ? v[i] - mean : 0.f;
+        q = fmaf(d, d, q);
+    }
+    for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q / (float)cnt + eps);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int idx = lane + 32 * i;
+        if (idx >= cnt) continue;
+        float o = (v[i] - mean) * rstd;
+        if (gamma) { const int c = g * cpg + idx / HW; o = fmaf(o, __ldg(gamma + c), __ldg(beta + c)); }
+        if (res) o += res[base + idx];
+        if (relu) o = fmaxf(o, 0.f);
+        y[base + idx] = o;
+    }
+}
+
+// large groups: statistics by many CTAs per group (fp32 block partials, fp64 atomics), then a flat apply pass
+__global__ void __launch_bounds__(256) k_norm_stats(const float *__restrict__ x, int C, int HW, int groups, int slices,
+                                                    double *__restrict__ stats) {
+    __shared__ float rs[8], rq[8];
+    const int gi = blockIdx.x / slices, sl = blockIdx.x % slices;
+    const int n = gi / groups, g = gi % groups, cpg = C / groups;
+    const size_t base = ((size_t)n * C + (size_t)g * cpg) * HW;
+    const int64_t cnt = (int64_t)cpg * HW;
+    const int64_t per = (cnt + slices - 1) / slices, lo = sl * per, hi = min(cnt, lo + per);
+    float s = 0.f, q = 0.f;
+    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) { const float t = x[base + i]; s += t; q = fmaf(t, t, q); }
+    for (int o = 16; o; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) { rs[wid] = s; rq[wid] = q; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double ds = 0.0, dq = 0.0;
+        for (int w = 0; w < 8; ++w) { ds += (double)rs[w]; dq += (double)rq[w]; }
+        atomicAdd(&stats[2 * gi], ds);
+        atomicAdd(&stats[2 * gi + 1], dq);
+    }
+}
+__global__ void k_norm_apply(const float *__restrict__ x, const double *__restrict__ stats, const float *__restrict__ gamma,
+                             const float *__restrict__ beta, const float *__restrict__ res, float *__restrict__ y, int C,
+                             int HW, int groups, float eps, int relu, int64_t total) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = (int)((i / HW) % C), n = (int)(i / ((int64_t)HW * C)), cpg = C / groups;
+    const int gi = n * groups + c / cpg;
+    const double cnt = (double)cpg * HW;
+    const double mean = stats[2 * gi] / cnt;
+    const double var = fmax(stats[2 * gi + 1] / cnt - mean * mean, 0.0);
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    float o = (x[i] - (float)mean) * rstd;
+    if (gamma) o = fmaf(o, __ldg(gamma + c), __ldg(beta + c));
+    if (res) o += res[i];
+    if (relu) o = fmaxf(o, 0.f);
+    y[i] = o;
+}
+
 // ---------------------------------------------------------------- pooling / resampling / joins
 __global__ void k_avg_pool2(const float *__restrict__ x, float *__restrict__ y, int64_t planes, int H, int W) {
     const int OH = H / 2, OW = W / 2;
@@ -302,11 +384,29 @@ extern "C" int icon_conv2d(const float *x, const float *w, const float *bias, co
 }
 
 extern "C" int icon_group_norm(const float *x, const float *gamma, const float *beta, const float *res, float *y,
-                               int N, int C, int HW, int groups, float eps, int relu, icon_stream_t stream_) {
+                               int N, int C, int HW, int groups, float eps, int relu, void *stats_ws,
+                               icon_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     ICON_CHECK_ARG(x && y && N > 0 && C > 0 && HW > 0 && groups > 0 && C % groups == 0, "icon_group_norm: bad argument");
     ICON_CHECK_ARG((gamma == nullptr) == (beta == nullptr), "icon_group_norm: gamma and beta go together");
-    k_group_norm<<<N * groups, 512, 0, stream>>>(x, gamma, beta, res, y, C, HW, groups, eps, relu);
+    const int64_t cnt = (int64_t)(C / groups) * HW;
+    const int ng = N * groups;
+    if (cnt <= 32 * 32) {
+        k_group_norm_warp<32><<<(ng + 7) / 8, 256, 0, stream>>>(x, gamma, beta, res, y, C, HW, groups, eps, relu, ng);
+    } else if (cnt <= 32 * 128 && ng >= 296) {
+        k_group_norm_warp<128><<<(ng + 7) / 8, 256, 0, stream>>>(x, gamma, beta, res, y, C, HW, groups, eps, relu, ng);
+    } else if (stats_ws && (int64_t)ng * 4 < 592) {
+        // few large groups: spread each over several CTAs
+        int slices = (int)min((int64_t)64, max((int64_t)1, (int64_t)1184 / ng));
+        ICON_CUDA(cudaMemsetAsync(stats_ws, 0, sizeof(double) * 2 * ng, stream));
+        k_norm_stats<<<ng * slices, 256, 0, stream>>>(x, C, HW, groups, slices, (double *)stats_ws);
+        ICON_LAUNCHED();
+        const int64_t total = (int64_t)N * C * HW;
+        k_norm_apply<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(x, (const double *)stats_ws, gamma, beta, res, y, C,
+                                                                          HW, groups, eps, relu, total);
+    } else {
+        k_group_norm<<<ng, 512, 0, stream>>>(x, gamma, beta, res, y, C, HW, groups, eps, relu);
+    }
     ICON_LAUNCHED();
     return ICON_OK;
 }

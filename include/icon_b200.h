@@ -192,7 +192,8 @@ int icon_conv2d_tc(const float *x, const void *wt_packed, const float *bias, con
                    int Cin, int H, int W, int Cout, int KH, int KW, int stride, int pad, int out_pad, int reflect,
                    int transposed, int act, int n_tile, int splits, void *ws, size_t ws_bytes, icon_stream_t stream);
 int icon_group_norm(const float *x, const float *gamma, const float *beta, const float *res, float *y, int N,
-                    int C, int HW, int groups, float eps, int relu, icon_stream_t stream);
+                    int C, int HW, int groups, float eps, int relu, void *stats_ws /* 16*N*groups bytes or NULL */,
+                    icon_stream_t stream);
 /* nn.Conv3d (B = 1, Cout <= 8, cubic kernel / stride / padding / dilation) followed by eval-mode BatchNorm3d
  * folded into per-channel (scale, shift), optional residual add and ReLU: the layers of PaMIR's VolumeEncoder
  * (lib/net/VE.py:96-183).  x [Cin,D,H,W], w [Cout,Cin,k,k,k], y [Cout,OD,OH,OW]. */
