@@ -27,7 +27,7 @@ if ROOT not in sys.path:
 
 GRID = 256
 MLP_FLOP_PER_POINT = 344602          # BASELINE.md section 2 (c0 = 13)
-TRAFFIC_MLP_BYTES = None             # filled from the committed ncu capture (profiles/), bytes per launch
+TRAFFIC_MLP_BYTES = 985417472        # dram read + write bytes per launch, ncu --set full (profiles/r1b_summary.md)
 WORKLOAD = "icon-filter, dense 256^3 cell-centre lattice (16,777,216 points), 1 image per GPU"
 
 
