@@ -109,8 +109,12 @@ def cpu_port_rate(sd, smpl_cpu, feat_cpu, n_sample, repeats=1):
     import oracle
     from oracle import query as OQ
     from icon_b200 import synthetic as S
-    threads = os.cpu_count() or 1
+    try:
+        threads = len(os.sched_getaffinity(0))          # cores this process may actually run on
+    except AttributeError:
+        threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
+    os.environ.setdefault("OMP_NUM_THREADS", str(threads))
     pts = S.lattice_points(GRID)
     stride = pts.shape[1] // n_sample
     sample = pts[:, ::stride][:, :n_sample].contiguous()
