@@ -10,50 +10,66 @@
 namespace icon {
 
 // ---------------------------------------------------------------- upsample + boundary + carry
-__device__ __forceinline__ float lerp3(const float *__restrict__ g, int R, int z0, int y0, int x0,
-                                       int z1, int y1, int x1, float lz, float ly, float lx, float bal,
-                                       float *valid) {
-    // torch upsample_trilinear3d (align_corners=True) nesting: w innermost, then h, then d
-    const size_t RR = (size_t)R * R;
-    float v000 = g[z0 * RR + (size_t)y0 * R + x0], v001 = g[z0 * RR + (size_t)y0 * R + x1];
-    float v010 = g[z0 * RR + (size_t)y1 * R + x0], v011 = g[z0 * RR + (size_t)y1 * R + x1];
-    float v100 = g[z1 * RR + (size_t)y0 * R + x0], v101 = g[z1 * RR + (size_t)y0 * R + x1];
-    float v110 = g[z1 * RR + (size_t)y1 * R + x0], v111 = g[z1 * RR + (size_t)y1 * R + x1];
-    const float mx = 1.f - lx, my = 1.f - ly, mz = 1.f - lz;
-#define ICON_TRI(a, b, c, d, e, f, g_, h)                                                        \
-    (__fadd_rn(__fmul_rn(mz, __fadd_rn(__fmul_rn(my, __fadd_rn(__fmul_rn(mx, a), __fmul_rn(lx, b))), \
-                                       __fmul_rn(ly, __fadd_rn(__fmul_rn(mx, c), __fmul_rn(lx, d))))), \
-               __fmul_rn(lz, __fadd_rn(__fmul_rn(my, __fadd_rn(__fmul_rn(mx, e), __fmul_rn(lx, f))), \
-                                       __fmul_rn(ly, __fadd_rn(__fmul_rn(mx, g_), __fmul_rn(lx, h)))))))
-    float out = ICON_TRI(v000, v001, v010, v011, v100, v101, v110, v111);
-    if (valid) {
-        float b000 = v000 > bal, b001 = v001 > bal, b010 = v010 > bal, b011 = v011 > bal;
-        float b100 = v100 > bal, b101 = v101 > bal, b110 = v110 > bal, b111 = v111 > bal;
-        *valid = ICON_TRI(b000, b001, b010, b011, b100, b101, b110, b111);
-    }
-#undef ICON_TRI
-    return out;
-}
+// torch upsample_trilinear3d with align_corners=True and R_out = 2 R_in - 1 has weights 0, 1/2, 1 only; the
+// nesting is w innermost, then h, then d, and a tap with weight 0 contributes exactly 0, so skipping it keeps the
+// result bit-identical:  lerp(a, b) = 0.5 a + 0.5 b on odd coordinates, a on even ones.
+__device__ __forceinline__ float half_sum(float a, float b) { return __fadd_rn(__fmul_rn(0.5f, a), __fmul_rn(0.5f, b)); }
 
-__global__ void k_grid_upsample(const float *__restrict__ in, const uint8_t *__restrict__ done_in, int Ri,
-                                float bal, float *__restrict__ out, uint8_t *__restrict__ boundary,
-                                uint8_t *__restrict__ done_out) {
+// one thread = output voxels (2i, 2i+1) of row (y, z); rows are flattened into the x grid dimension
+__global__ void __launch_bounds__(256) k_grid_upsample(const float *__restrict__ in, const uint8_t *__restrict__ done_in,
+                                                       int Ri, float bal, float *__restrict__ out,
+                                                       uint8_t *__restrict__ boundary, uint8_t *__restrict__ done_out) {
     const int Ro = 2 * Ri - 1;
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y, z = blockIdx.z;
-    if (x >= Ro) return;
-    const int x0 = x >> 1, y0 = y >> 1, z0 = z >> 1;
-    const int x1 = min(x0 + 1, Ri - 1), y1 = min(y0 + 1, Ri - 1), z1 = min(z0 + 1, Ri - 1);
-    const float lx = (x & 1) ? 0.5f : 0.f, ly = (y & 1) ? 0.5f : 0.f, lz = (z & 1) ? 0.5f : 0.f;
-    float valid;
-    float v = lerp3(in, Ri, z0, y0, x0, z1, y1, x1, lz, ly, lx, bal, boundary ? &valid : nullptr);
-    const size_t o = ((size_t)z * Ro + y) * Ro + x;
-    out[o] = v;
-    if (boundary) boundary[o] = (valid > 0.f && valid < 1.f) ? 1 : 0;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = t % Ri, y = t / Ri, z = blockIdx.y;
+    if (y >= Ro) return;
+    const int y0 = y >> 1, z0 = z >> 1;
+    const bool oy = y & 1, oz = z & 1;
+    const int i1 = min(i + 1, Ri - 1);
+    const size_t RR = (size_t)Ri * Ri;
+    const float *r00 = in + z0 * RR + (size_t)y0 * Ri;
+    const float *r01 = r00 + (oy ? Ri : 0), *r10 = r00 + (oz ? RR : 0), *r11 = r10 + (oy ? Ri : 0);
+    // taps at x index i and i+1 for the (up to) four contributing input rows
+    const float a00 = r00[i], b00 = r00[i1];
+    float e, o;                      // outputs at x = 2i (even) and x = 2i+1 (odd)
+    bool any1, any0, any1o, any0o;   // boundary = some contributing tap above `bal` and some not
+    {
+        const bool pa = a00 > bal, pb = b00 > bal;
+        e = a00; o = half_sum(a00, b00);
+        any1 = pa; any0 = !pa; any1o = pa | pb; any0o = !pa | !pb;
+    }
+    if (oy) {
+        const float a = r01[i], b = r01[i1];
+        const bool pa = a > bal, pb = b > bal;
+        e = half_sum(e, a); o = half_sum(o, half_sum(a, b));
+        any1 |= pa; any0 |= !pa; any1o |= pa | pb; any0o |= !pa | !pb;
+    }
+    if (oz) {
+        const float a = r10[i], b = r10[i1];
+        bool pa = a > bal, pb = b > bal;
+        float e2 = a, o2 = half_sum(a, b);
+        any1 |= pa; any0 |= !pa; any1o |= pa | pb; any0o |= !pa | !pb;
+        if (oy) {
+            const float c = r11[i], d = r11[i1];
+            pa = c > bal; pb = d > bal;
+            e2 = half_sum(e2, c); o2 = half_sum(o2, half_sum(c, d));
+            any1 |= pa; any0 |= !pa; any1o |= pa | pb; any0o |= !pa | !pb;
+        }
+        e = half_sum(e, e2); o = half_sum(o, o2);
+    }
+    const size_t ob = ((size_t)z * Ro + y) * Ro + 2 * i;
+    const bool has_odd = 2 * i + 1 < Ro;
+    out[ob] = e;
+    if (has_odd) out[ob + 1] = o;
+    if (boundary) {
+        boundary[ob] = (any1 && any0) ? 1 : 0;
+        if (has_odd) boundary[ob + 1] = (any1o && any0o) ? 1 : 0;
+    }
     if (done_out) {
         uint8_t d = 0;
-        if (!((x | y | z) & 1)) d = done_in ? done_in[((size_t)z0 * Ri + y0) * Ri + x0] : 1;
-        done_out[o] = d;
+        if (!oy && !oz) d = done_in ? done_in[z0 * RR + (size_t)y0 * Ri + i] : 1;
+        done_out[ob] = d;
+        if (has_odd) done_out[ob + 1] = 0;
     }
 }
 
@@ -163,8 +179,8 @@ extern "C" int icon_grid_upsample(const float *occ_in, const uint8_t *done_in, i
     cudaStream_t stream = (cudaStream_t)stream_;
     ICON_CHECK_ARG(occ_in && occ_out && R_in >= 2 && R_in <= 32768, "icon_grid_upsample: bad argument (R_in=%d)", R_in);
     const int Ro = 2 * R_in - 1;
-    dim3 grid((Ro + 127) / 128, Ro, Ro);
-    k_grid_upsample<<<grid, 128, 0, stream>>>(occ_in, done_in, R_in, balance, occ_out, boundary, done_out);
+    dim3 grid((unsigned)(((int64_t)Ro * R_in + 255) / 256), Ro);
+    k_grid_upsample<<<grid, 256, 0, stream>>>(occ_in, done_in, R_in, balance, occ_out, boundary, done_out);
     ICON_LAUNCHED();
     return ICON_OK;
 }
