@@ -274,11 +274,13 @@ __global__ void __launch_bounds__(SW_T) k_sdf_warp(const float4 *__restrict__ xy
     {
         float sbA = best * rsqrtf(best) * 1.00001f + 1e-6f;    // ~sqrt(best), inflated; bounds only
         const float ubA = ubw2 * 1.00001f + 1e-6f;
-        auto lane_test = [&](int k, float4 s, float4 r0, float4 r1, float4 r2) {
+        // `tr` points at the face's three float4 (a, ab, ac); it is only dereferenced once the sphere test passes
+        auto lane_test = [&](int k, float4 s, const float4 *tr) {
             const float dx = p.x - s.x, dy = p.y - s.y, dz = p.z - s.z;
             const float dd = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
             const float l = sbA + s.w;
             if (dd > l * l) return;                            // sphere bound beats this lane's best
+            const float4 r0 = tr[0], r1 = tr[1], r2 = tr[2];
             const V3 ab = mk3(r0.w, r1.x, r1.y), ac = mk3(r1.z, r1.w, r2.x);
             const float S1 = fmaf(dz, ab.z, fmaf(dy, ab.y, dx * ab.x));
             const float T1 = fmaf(dz, ac.z, fmaf(dy, ac.y, dx * ac.x));
@@ -286,8 +288,9 @@ __global__ void __launch_bounds__(SW_T) k_sdf_warp(const float4 *__restrict__ xy
             const float g = dd - M - 1e-7f;                    // |w|^2 - |w| h(u)
             if (g > 0.f && g * g > best * dd * 1.0001f) return;   // support bound beats this lane's best
             const float d = tri_sqdist(p, mk3(r0.x, r0.y, r0.z), ab, ac);
+            if (d > best) return;
             const int f = __ldg(m.order + k);
-            if (d < best || (d == best && f < bi)) {
+            if (d < best || f < bi) {
                 best = d; bi = f;
                 sbA = d * rsqrtf(d) * 1.00001f + 1e-6f;
                 if (!(d > 0.f)) sbA = 1e-6f;
@@ -318,13 +321,12 @@ __global__ void __launch_bounds__(SW_T) k_sdf_warp(const float4 *__restrict__ xy
                     S.tri[at][0] = __ldg(tp); S.tri[at][1] = __ldg(tp + 1); S.tri[at][2] = __ldg(tp + 2);
                 }
                 __syncwarp();
-                for (int j = 0; j < cnt; ++j) lane_test(S.kk[j], S.sph[j], S.tri[j][0], S.tri[j][1], S.tri[j][2]);
+                for (int j = 0; j < cnt; ++j) lane_test(S.kk[j], S.sph[j], &S.tri[j][0]);
                 __syncwarp();
             }
         } else {
             for (int k = 0; k < m.F; ++k) {
-                const float4 *tp = m.tri_s + 3 * (size_t)k;
-                lane_test(k, __ldg(m.sph_s + k), __ldg(tp), __ldg(tp + 1), __ldg(tp + 2));
+                lane_test(k, __ldg(m.sph_s + k), m.tri_s + 3 * (size_t)k);
             }
         }
     }

@@ -1,3 +1,10 @@
+"""Candidate statistics of k_sdf_warp (overflowing warps, leaves and faces per warp).
+
+Needs a debug build of the library with the counters compiled in:
+    cd icon_b200/csrc && for f in *.cu; do nvcc -c $f -o /tmp/dbg_${f%.cu}.o -gencode arch=compute_100a,code=sm_100a \
+        -O3 -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr -DICON_SDF_STATS $( [ $f = sdf.cu -o $f = smpl.cu ] && echo -fmad=false ); done
+    nvcc -shared -o build/libicon_dbg.so /tmp/dbg_*.o -gencode arch=compute_100a,code=sm_100a -lcudart
+"""
 import sys, os, ctypes
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import icon_b200._C as C
