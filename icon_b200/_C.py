@@ -32,6 +32,7 @@ _SIGS = {
     "icon_get_mlp_impl": (_i, []),
     "icon_query": (_i, [_i, _vp, _i64, _i64, _i64, _vp, _vp, _i, _i, _i, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _f,
                         _vp, _vp, _sz, _vp]),
+    "icon_set_sdf_policy": (_i, [_i, _i64, _i64]),
     "icon_sdf_only": (_i, [_vp, _i64, _i64, _i64, _vp, _vp, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "icon_sdf_bruteforce": (_i, [_vp, _i64, _i64, _i64, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "icon_mlp_only": (_i, [_vp, _i, _i64, _vp, _vp, _vp, _vp]),

@@ -77,7 +77,9 @@ __device__ __forceinline__ void emit_record(V3 p, int bi, float best, int hits, 
 constexpr int SW_T = 128;               // 4 warps per block, one warp = 32 Morton-adjacent points
 constexpr int NBIN_AX = 128;            // Morton bins per axis over [-1,1]^3 (+1 overflow bin)
 constexpr int NBIN = NBIN_AX * NBIN_AX * NBIN_AX;
-constexpr int FR_CAP = 1536;            // frontier / leaf list capacity per warp
+// frontier / leaf list capacity per warp: the fewer points a warp carries the tighter its box and the shorter the
+// lists, and the smaller footprint lets more warps be resident to hide the tree walk's dependent loads
+__host__ __device__ constexpr int fr_cap(int ppw) { return ppw >= 16 ? 1024 : (ppw >= 4 ? 768 : 384); }
 
 __device__ __forceinline__ float box_dist2(V3 p, float4 lo, float4 hi) {
     float dx = fmaxf(fmaxf(lo.x - p.x, p.x - hi.x), 0.f);
@@ -156,6 +158,7 @@ __device__ unsigned long long g_stats[8];   // warps, overflow warps, sum leaves
 #define STAT(i, v) do { } while (0)
 #endif
 
+template <int FR_CAP>
 struct WarpSmem {
     unsigned short fr[2][FR_CAP];      // node / leaf ids (leaf count <= 65535 is checked by the host)
     float4 sph[32];                    // bounding spheres of the surviving faces of the current chunk (compacted)
@@ -170,14 +173,24 @@ __device__ __forceinline__ float box_far2(V3 p, float4 lo, float4 hi) {   // squ
     return fmaf(dz, dz, fmaf(dy, dy, dx * dx));
 }
 
+// PPW = query points per warp; each point is replicated on REP = 32/PPW lanes which split the candidate faces
+// (and the ray list) between them and merge by shuffle.  32: one point per lane, for dense sets where 32 Morton-
+// consecutive points fill a small box.  8 / 1: for the engine's sparse refinement sets, where 32 consecutive points
+// span a large box and the shared candidate list explodes; with PPW = 1 the warp box is a point, the lists are the
+// per-point minimum and the 32 lanes only share the work.  The kernel is bound by the latency of the dependent
+// tree loads, so the shared-memory footprint (fr_cap) is kept small enough for >= 36 resident warps per SM.
+template <int PPW>
 __global__ void __launch_bounds__(SW_T) k_sdf_warp(const float4 *__restrict__ xyz4, const int32_t *__restrict__ perm,
                                                    int64_t N, MeshView m, float *__restrict__ rec,
                                                    int32_t *__restrict__ face) {
+    constexpr int REP = 32 / PPW;
+    constexpr int FR_CAP = fr_cap(PPW);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    WarpSmem &S = reinterpret_cast<WarpSmem *>(smem_raw)[wib];
-    const int64_t pos = ((int64_t)blockIdx.x * (SW_T / 32) + wib) * 32 + lane;
-    const int64_t pos0 = pos - lane;
+    WarpSmem<FR_CAP> &S = reinterpret_cast<WarpSmem<FR_CAP> *>(smem_raw)[wib];
+    const int sub = lane % PPW, rep_id = lane / PPW;           // which point of the warp, which replica
+    const int64_t pos0 = ((int64_t)blockIdx.x * (SW_T / 32) + wib) * PPW;
+    const int64_t pos = pos0 + sub;
     if (pos0 >= N) return;                                   // whole warp out of range
     const bool live = pos < N;
     const int64_t idx = perm[live ? pos : pos0];
@@ -321,12 +334,29 @@ __global__ void __launch_bounds__(SW_T) k_sdf_warp(const float4 *__restrict__ xy
                     S.tri[at][0] = __ldg(tp); S.tri[at][1] = __ldg(tp + 1); S.tri[at][2] = __ldg(tp + 2);
                 }
                 __syncwarp();
-                for (int j = 0; j < cnt; ++j) lane_test(S.kk[j], S.sph[j], &S.tri[j][0]);
+                for (int j = rep_id; j < cnt; j += REP) lane_test(S.kk[j], S.sph[j], &S.tri[j][0]);
+                if (REP > 1) {                                  // replicas of a point share their best
+#pragma unroll
+                    for (int o = PPW; o < 32; o <<= 1) {
+                        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+                        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                        if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+                    }
+                    sbA = best > 0.f ? best * rsqrtf(best) * 1.00001f + 1e-6f : 1e-6f;
+                }
                 __syncwarp();
             }
         } else {
-            for (int k = 0; k < m.F; ++k) {
+            for (int k = rep_id; k < m.F; k += REP) {
                 lane_test(k, __ldg(m.sph_s + k), m.tri_s + 3 * (size_t)k);
+            }
+        }
+        if (REP > 1) {                                          // final merge over the replicas (ties: lowest face id)
+#pragma unroll
+            for (int o = PPW; o < 32; o <<= 1) {
+                const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
             }
         }
     }
@@ -338,7 +368,7 @@ __global__ void __launch_bounds__(SW_T) k_sdf_warp(const float4 *__restrict__ xy
         if (fy >= 0.f && fy < (float)RAY_GRID && fz >= 0.f && fz < (float)RAY_GRID) {
             const int cc = (int)fz * RAY_GRID + (int)fy;
             const int k0 = __ldg(m.roff + cc), k1 = __ldg(m.roff + cc + 1);
-            for (int k = k0; k < k1; ++k) {
+            for (int k = k0 + rep_id; k < k1; k += REP) {
                 const int f = __ldg(m.rlist + k);
                 if (__ldg(&m.rbox[2 * (size_t)f + 1].x) < p.x - 1e-3f) continue;     // wholly behind the ray origin
                 const Tri tr = load_tri(m.tri + 3 * (size_t)f);
@@ -346,12 +376,16 @@ __global__ void __launch_bounds__(SW_T) k_sdf_warp(const float4 *__restrict__ xy
             }
         }
     } else {
-        for (int f = 0; f < m.F; ++f) {
+        for (int f = rep_id; f < m.F; f += REP) {
             const Tri tr = load_tri(m.tri + 3 * (size_t)f);
             hits += ray_hit_px(p, tr.a, tr.ab, tr.ac);
         }
     }
-    if (live) emit_record(p, bi, best, hits, m, rec, face, idx);
+    if (REP > 1) {
+#pragma unroll
+        for (int o = PPW; o < 32; o <<= 1) hits += __shfl_xor_sync(0xffffffffu, hits, o);
+    }
+    if (live && rep_id == 0) emit_record(p, bi, best, hits, m, rec, face, idx);
 }
 
 // brute force: every point against every face, faces staged through shared memory
@@ -382,6 +416,10 @@ __global__ void __launch_bounds__(256) k_sdf_brute(const float *__restrict__ pts
     }
     if (live) emit_record(p, bi, best, hits, m, rec, face, i);
 }
+
+// points-per-warp policy of k_sdf_warp (see its header comment); icon_set_sdf_policy() overrides it for tuning
+static int64_t g_sdf_ppw32_from = 6000000, g_sdf_ppw8_from = 300000;
+static int g_sdf_ppw_force = 0;
 
 // ---------------------------------------------------------------- host-side pipeline pieces
 struct SdfWs {
@@ -433,13 +471,32 @@ int run_sdf(const float *points, int64_t sc, int64_t sn, int64_t N, const float 
     k_points_scatter<<<nblk, 256, 0, stream>>>(w.bid, N, w.offset, w.count, w.perm);
     ICON_LAUNCHED();
     static bool attr_set = false;
-    const int smem = (int)(sizeof(WarpSmem) * (SW_T / 32));
     if (!attr_set) {
-        ICON_CUDA(cudaFuncSetAttribute(k_sdf_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+#define ICON_SDF_ATTR(P) ICON_CUDA(cudaFuncSetAttribute(k_sdf_warp<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                                        (int)(sizeof(WarpSmem<fr_cap(P)>) * (SW_T / 32))))
+        ICON_SDF_ATTR(32); ICON_SDF_ATTR(16); ICON_SDF_ATTR(8); ICON_SDF_ATTR(4); ICON_SDF_ATTR(2); ICON_SDF_ATTR(1);
+#undef ICON_SDF_ATTR
         attr_set = true;
     }
     profile_mark(1, stream);
-    k_sdf_warp<<<(unsigned)((N + SW_T - 1) / SW_T), SW_T, smem, stream>>>(w.xyz4, w.perm, N, m, rec, face);
+    // measured on the engine's own query sets (profiles/r1c_summary.md): 36k / 167k points -> PPW 1 wins,
+    // 826k -> PPW 8, the dense 257^3 lattice -> PPW 32
+    int ppw = N >= g_sdf_ppw32_from ? 32 : (N >= g_sdf_ppw8_from ? 8 : 1);
+    if (g_sdf_ppw_force) ppw = g_sdf_ppw_force;
+    const int wpb = SW_T / 32;
+    const int64_t nwarps = (N + ppw - 1) / ppw;
+    const unsigned nblk_w = (unsigned)((nwarps + wpb - 1) / wpb);
+#define ICON_SDF_LAUNCH(P) k_sdf_warp<P><<<nblk_w, SW_T, sizeof(WarpSmem<fr_cap(P)>) * (SW_T / 32), stream>>>( \
+        w.xyz4, w.perm, N, m, rec, face)
+    switch (ppw) {
+        case 32: ICON_SDF_LAUNCH(32); break;
+        case 16: ICON_SDF_LAUNCH(16); break;
+        case 8: ICON_SDF_LAUNCH(8); break;
+        case 4: ICON_SDF_LAUNCH(4); break;
+        case 2: ICON_SDF_LAUNCH(2); break;
+        default: ICON_SDF_LAUNCH(1); break;
+    }
+#undef ICON_SDF_LAUNCH
     ICON_LAUNCHED();
     profile_mark(2, stream);
     if (xyz4_out) *xyz4_out = w.xyz4;
@@ -475,6 +532,14 @@ extern "C" int icon_debug_sdf_stats(unsigned long long *out, int reset) {
     return 0;
 }
 #endif
+
+extern "C" int icon_set_sdf_policy(int force_ppw, int64_t ppw8_from, int64_t ppw32_from) {
+    ICON_CHECK_ARG(force_ppw >= 0 && force_ppw <= 32 && (force_ppw & (force_ppw - 1)) == 0, "icon_set_sdf_policy: ppw in {0,1,2,4,8,16,32}");
+    icon::g_sdf_ppw_force = force_ppw;
+    if (ppw8_from >= 0) icon::g_sdf_ppw8_from = ppw8_from;
+    if (ppw32_from >= 0) icon::g_sdf_ppw32_from = ppw32_from;
+    return ICON_OK;
+}
 
 extern "C" int icon_sdf_only(const float *points, int64_t stride_c, int64_t stride_n, int64_t N,
                              const float *h_calib, const void *mesh_ws, int V, int F, float *rec,

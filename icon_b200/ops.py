@@ -172,6 +172,11 @@ def set_mlp_impl(name):
     check(lib.icon_set_mlp_impl({"fp32": 0, "tcgen05": 1}[name]), "icon_set_mlp_impl")
 
 
+def set_sdf_policy(force_ppw=0, ppw8_from=-1, ppw32_from=-1):
+    """Points-per-warp policy of the SDF kernel (include/icon_b200.h: icon_set_sdf_policy); 0 = automatic."""
+    check(lib.icon_set_sdf_policy(int(force_ppw), int(ppw8_from), int(ppw32_from)), "icon_set_sdf_policy")
+
+
 # --------------------------------------------------------------------------- query
 def _point_strides(points):
     """points [1,3,N] (any strides) -> (tensor, stride_c, stride_n, N) in elements."""

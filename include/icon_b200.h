@@ -108,6 +108,10 @@ int icon_query(int prior, const float *points, int64_t stride_c, int64_t stride_
                const float *mlp_packed, const void *mlp_tc, int c0, float sdf_clip, float *out,
                void *ws, size_t ws_bytes, icon_stream_t stream);
 
+/* Points-per-warp policy of the SDF kernel: force_ppw in {1, 8, 32} pins it (0 = automatic: 1 below ppw8_from
+ * points per call, 8 below ppw32_from, else 32; negative thresholds keep the current value). */
+int icon_set_sdf_policy(int force_ppw, int64_t ppw8_from, int64_t ppw32_from);
+
 /* Debug / parity tap: the SMPL block alone (cal_sdf_batch outputs before the outlier rule).
  * rec [N,8] f32 = sdf, cmap xyz, norm xyz, vis(0/1); face [N] i32 nearest face id. */
 int icon_sdf_only(const float *points, int64_t stride_c, int64_t stride_n, int64_t N,

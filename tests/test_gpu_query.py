@@ -53,10 +53,21 @@ def _rec_from_oracle(verts, faces, cmap, vis, pts):
     return rec, face
 
 
+@pytest.fixture
+def sdf_policy():
+    from icon_b200 import ops
+    yield ops.set_sdf_policy
+    ops.set_sdf_policy(0)
+
+
+@pytest.mark.parametrize("ppw", [0, 1, 2, 4, 8, 16, 32])
 @pytest.mark.parametrize("kind", ["random", "lattice", "faces_and_outside"])
-def test_sdf_block_bit_exact_vs_oracle(kind):
+def test_sdf_block_bit_exact_vs_oracle(kind, ppw, sdf_policy, mlp_impl):
+    if mlp_impl != "tcgen05":
+        pytest.skip("SDF block does not depend on the MLP implementation")
     dev = _cuda()
     from icon_b200 import ops
+    sdf_policy(ppw)
     verts, faces, cmap, vis = _mesh()
     if kind == "random":
         pts = _points(12000, seed=1)
@@ -78,9 +89,11 @@ def test_sdf_block_bit_exact_vs_oracle(kind):
     assert torch.equal(rec[:, 1:7], ref_rec[:, 1:7]), "cmap / normal not bit-exact"
 
 
-def test_sdf_bricks_equal_bruteforce_kernel():
+@pytest.mark.parametrize("ppw", [1, 8, 32])
+def test_sdf_bricks_equal_bruteforce_kernel(ppw, sdf_policy):
     dev = _cuda()
     from icon_b200 import ops
+    sdf_policy(ppw)
     verts, faces, cmap, vis = _mesh()
     body = ops.SmplBody(verts.to(dev), faces.to(dev), cmap.to(dev), vis.to(dev))
     pts = S.lattice_points(64).permute(0, 2, 1).contiguous().to(dev)       # 262144 points
