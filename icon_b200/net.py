@@ -11,10 +11,13 @@ lib/net/*.py and lib/common/train_util.py.
   HGPIFuNet      lib/net/HGPIFuNet.py:34-410   (filter / query / get_normal; eval path)
   query_func     lib/common/train_util.py:324-348
 """
+import os
+
 import torch
 import torch.nn as nn
 
 from . import ops
+from .voxelize import Voxelization, read_smpl_constants
 from .encoders import HGFilter, NormalNet, VolumeEncoder
 
 
@@ -154,6 +157,12 @@ class HGPIFuNet(BasePIFuNet):
             channels_IF[0] += self.smpl_dim
         elif self.prior_type == "pamir":
             channels_IF[0] += self.voxel_dim
+            # HGPIFuNet.py:107-118: constants come from <data>/tedra_data (SMPLX().tedra_dir); they are licensed
+            # assets that may be absent, in which case set_smpl_constants() supplies them before the first filter()
+            self.voxelization = None
+            tedra_dir = getattr(cfg, "tedra_dir", os.path.join(self.root, "tedra_data"))
+            if os.path.exists(os.path.join(tedra_dir, "vertices.txt")):
+                self.set_smpl_constants(*read_smpl_constants(tedra_dir), batch_size=getattr(cfg, "batch_size", 1))
             self.ve = VolumeEncoder(3, self.voxel_dim, self.opt.num_stack)
         else:
             channels_IF[0] += 1
@@ -174,6 +183,31 @@ class HGPIFuNet(BasePIFuNet):
         self._body = None
         self._body_key = None
         self._vol_feat = None
+        self._vol_key = None
+
+    def set_smpl_constants(self, smpl_vertex_code, smpl_face_code, smpl_faces, smpl_tetras, batch_size=1):
+        """What the reference's constructor does with read_smpl_constants() (HGPIFuNet.py:107-118)."""
+        self.voxelization = Voxelization(smpl_vertex_code, smpl_face_code, smpl_faces, smpl_tetras, volume_res=128,
+                                         sigma=0.05, smooth_kernel_size=7, batch_size=batch_size, device="cuda")
+
+    def _pamir_volume_feature(self):
+        """HGPIFuNet.py:314-325: strip the padding, voxelise, encode.  The reference redoes this on every query
+        call; the result only depends on the subject, so it is cached on (data_ptr, _version) of voxel_verts."""
+        d = self.smpl_feat_dict or {}
+        if "voxel_verts" not in d or self.voxelization is None:
+            return None
+        vv, vf = d["voxel_verts"], d["voxel_faces"]
+        key = (vv.data_ptr(), vv._version, vf.data_ptr(), vf._version)
+        if self._vol_key != key:
+            pv, pf = int(d["pad_v_num"][0]), int(d["pad_f_num"][0])
+            verts = vv[:, :-pv, :] if pv > 0 else vv
+            tets = vf[:, :-pf, :] if pf > 0 else vf
+            self.voxelization.device = verts.device
+            self.voxelization.update_param(batch_size=tets.shape[0], smpl_tetra=tets[0])
+            vol = self.voxelization(verts)
+            self._vol_feat = self.ve(vol, intermediate_output=False)[-1]
+            self._vol_key = key
+        return self._vol_feat
 
     # ------------------------------------------------------------------ filter
     def get_normal(self, in_tensor_dict):
@@ -219,6 +253,7 @@ class HGPIFuNet(BasePIFuNet):
             self.smpl_feat_dict = {k: in_tensor_dict[k] for k in self.icon_keys}
         elif self.prior_type == "pamir":
             self.smpl_feat_dict = {k: in_tensor_dict[k] for k in self.pamir_keys if k in in_tensor_dict}
+            self._vol_feat, self._vol_key = None, None
             if "vol_feat" in in_tensor_dict:      # pre-encoded volume feature
                 self._vol_feat = in_tensor_dict["vol_feat"]
             elif "vol" in in_tensor_dict:         # semantic volume [1,3,128,128,128] -> VolumeEncoder, once per subject
@@ -257,11 +292,11 @@ class HGPIFuNet(BasePIFuNet):
         body = self._prepared_body() if self.prior_type == "icon" else None
         vol = None
         if self.prior_type == "pamir":
-            vol = self._vol_feat
+            vol = self._vol_feat if self._vol_feat is not None and self._vol_key is None else self._pamir_volume_feature()
             if vol is None:
-                raise NotImplementedError("pamir prior: pass in_tensor_dict['vol'] (semantic volume) or a pre-encoded "
-                                          "in_tensor_dict['vol_feat'] to filter(); the voxelisation kernel itself "
-                                          "(voxelize_cuda, source absent) is not restated (DESIGN.md section 7)")
+                raise RuntimeError("pamir prior: filter() needs voxel_verts / voxel_faces / pad_v_num / pad_f_num "
+                                   "(plus SMPL constants: <root>/tedra_data or set_smpl_constants()), or a semantic "
+                                   "volume 'vol', or a pre-encoded 'vol_feat'")
         with torch.no_grad():
             for im_feat in features:
                 preds = ops.query(self.prior_type, points, calibs, im_feat, regressor.packed(),

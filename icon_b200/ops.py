@@ -327,3 +327,21 @@ def marching_cubes(occ, iso=0.5):
     check(lib.icon_mc_emit(_p(o), R, float(iso), padded, _p(ws), _p(verts), _p(faces), nv, nt, _stream()),
           "icon_mc_emit")
     return verts, faces
+
+
+# --------------------------------------------------------------------------- PaMIR semantic voxelisation
+def voxelize(verts, n_surface, codes, tets, res, sigma):
+    """verts [NV,3] f32 (surface vertices first), codes [n_surface,3] f32, tets [NT,4] int -> [1,3,res,res,res]
+    (b, c, z, y, x) semantic volume; include/icon_b200.h: icon_voxelize."""
+    _need_cuda(verts)
+    v = verts.detach().float().contiguous()
+    c = codes.detach().float().contiguous().to(v.device)
+    t = tets.detach().to(device=v.device, dtype=torch.int32).contiguous()
+    if v.dim() != 2 or v.shape[1] != 3 or c.shape != (n_surface, 3) or t.dim() != 2 or t.shape[1] != 4:
+        raise _C.IconError(f"voxelize: verts {tuple(v.shape)}, codes {tuple(c.shape)}, tets {tuple(t.shape)}")
+    out = torch.empty(1, 3, res, res, res, dtype=torch.float32, device=v.device)
+    nbytes = lib.icon_voxelize_workspace_bytes(res)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=v.device)
+    check(lib.icon_voxelize(_p(v), v.shape[0], int(n_surface), _p(c), _p(t), t.shape[0], int(res), float(sigma),
+                            _p(out), _p(ws), nbytes, _stream()), "icon_voxelize")
+    return out

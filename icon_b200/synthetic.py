@@ -133,3 +133,16 @@ def seeded_like(state_dict, seed):
         else:
             out[k] = 0.1 * torch.randn(shape, generator=g)
     return out
+
+
+def tet_body(rings=82, segs=84, seed=0, extent=(0.22, 0.42, 0.12)):
+    """Tetra-SMPL stand-in (what TestDataset.compute_voxel_verts hands to the pamir prior): the star-shaped
+    body_mesh inside [-0.5,0.5]^3 plus one interior vertex at the origin, every face joined to it.
+    Returns (verts [V+1,3] f32, n_surface V, tets [F,4] int32, vertex_code [V,3] f32 in [0,1])."""
+    verts, faces = body_mesh(rings, segs, seed, extent)
+    V = len(verts)
+    allv = np.concatenate([verts, np.zeros((1, 3), np.float32)], 0)
+    tets = np.concatenate([faces.astype(np.int32), np.full((len(faces), 1), V, np.int32)], 1)
+    lo, hi = verts.min(0, keepdims=True), verts.max(0, keepdims=True)
+    code = ((verts - lo) / (hi - lo)).astype(np.float32)
+    return allv.astype(np.float32), V, tets, code

@@ -175,6 +175,16 @@ int icon_mc_count(const float *occ, int R, float iso, int padded, void *ws, size
 int icon_mc_emit(const float *occ, int R, float iso, int padded, const void *ws, void *verts,
                  int64_t *faces, int64_t n_verts, int64_t n_tris, icon_stream_t stream);
 
+/* ------------------------------------------------------------------ PaMIR semantic voxelisation
+ * Replaces voxelize_cuda.forward_semantic_voxelization as called by VoxelizationFunction.forward
+ * (lib/net/voxelize.py:57-59) plus the bzyxc -> bcdhw permute of Voxelization.forward (:137).
+ * verts [NV,3] f32 (surface vertices first, then the tetra-SMPL interior ones, in [-0.5,0.5]^3),
+ * codes [NVsurf,3] f32, tets [NT,4] i32 (indices into verts), out [3,res,res,res] f32 (c,z,y,x).
+ * Source of voxelize_cuda is absent: the algorithm is restated (csrc/voxelize.cu header), parity unpinned. */
+size_t icon_voxelize_workspace_bytes(int res);
+int icon_voxelize(const float *verts, int NV, int NVsurf, const float *codes, const int32_t *tets, int NT,
+                  int res, float sigma, float *out, void *ws, size_t ws_bytes, icon_stream_t stream);
+
 /* ------------------------------------------------------------------ encoder operators (NCHW fp32)
  * Replace the cuDNN / torch calls inside HGFilter (lib/net/HGFilters.py:161-197, ConvBlock
  * lib/net/net_util.py:258-280), GlobalGenerator / ResnetBlock (lib/net/FBNet.py:216-319) and
