@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(SW_T) k_sdf_warp(const float4 *__restrict__ xy
     //      the exact distance.
     {
         float sbA = best * rsqrtf(best) * 1.00001f + 1e-6f;    // ~sqrt(best), inflated; bounds only
-        const float ubA = ubw2 * 1.00001f + 1e-6f;
+        float ubA = ubw2 * 1.00001f + 1e-6f;
         // `tr` points at the face's three float4 (a, ab, ac); it is only dereferenced once the sphere test passes
         auto lane_test = [&](int k, float4 s, const float4 *tr) {
             const float dx = p.x - s.x, dy = p.y - s.y, dz = p.z - s.z;
@@ -344,6 +344,7 @@ __global__ void __launch_bounds__(SW_T) k_sdf_warp(const float4 *__restrict__ xy
                     }
                     sbA = best > 0.f ? best * rsqrtf(best) * 1.00001f + 1e-6f : 1e-6f;
                 }
+                ubA = fminf(ubA, warp_max(sbA));               // the lanes' bounds only shrink: cull the next chunk harder
                 __syncwarp();
             }
         } else {
@@ -418,7 +419,7 @@ __global__ void __launch_bounds__(256) k_sdf_brute(const float *__restrict__ pts
 }
 
 // points-per-warp policy of k_sdf_warp (see its header comment); icon_set_sdf_policy() overrides it for tuning
-static int64_t g_sdf_ppw32_from = 6000000, g_sdf_ppw8_from = 300000;
+static int64_t g_sdf_ppw32_from = 1300000, g_sdf_ppw8_from = 300000;
 static int g_sdf_ppw_force = 0;
 
 // ---------------------------------------------------------------- host-side pipeline pieces
@@ -479,8 +480,9 @@ int run_sdf(const float *points, int64_t sc, int64_t sn, int64_t N, const float 
         attr_set = true;
     }
     profile_mark(1, stream);
-    // measured on the engine's own query sets (profiles/r1c_summary.md): 36k / 167k points -> PPW 1 wins,
-    // 826k -> PPW 8, the dense 257^3 lattice -> PPW 32
+    // the kernel needs >= ~50k warps to hide the latency of its tree walk, so the fewer points a call has the fewer
+    // of them a warp carries.  Measured (profiles/r1c_summary.md): 36k / 167k points -> PPW 1 wins, 826k -> PPW 8,
+    // 2.1M (dense 128^3) and up -> PPW 32
     int ppw = N >= g_sdf_ppw32_from ? 32 : (N >= g_sdf_ppw8_from ? 8 : 1);
     if (g_sdf_ppw_force) ppw = g_sdf_ppw_force;
     const int wpb = SW_T / 32;

@@ -109,7 +109,8 @@ int icon_query(int prior, const float *points, int64_t stride_c, int64_t stride_
                void *ws, size_t ws_bytes, icon_stream_t stream);
 
 /* Points-per-warp policy of the SDF kernel: force_ppw in {1, 8, 32} pins it (0 = automatic: 1 below ppw8_from
- * points per call, 8 below ppw32_from, else 32; negative thresholds keep the current value). */
+ * points per call, 8 below ppw32_from, else 32; negative thresholds keep the current value).  Results are
+ * identical for every setting. */
 int icon_set_sdf_policy(int force_ppw, int64_t ppw8_from, int64_t ppw32_from);
 
 /* Debug / parity tap: the SMPL block alone (cal_sdf_batch outputs before the outlier rule).
