@@ -42,7 +42,7 @@ for mc in (256, 512):
     ms_mc, (v, f) = timed(lambda: ops.marching_cubes(occ, 0.5))
     ms_exp, _ = timed(lambda: eng.export_mesh(occ), n=3, warm=1)
     G = R + 1 if (R - 1) <= 256 else R - 1
-    mc_bytes = G ** 3 * (4 + 10 + 10) + v.numel() * v.element_size() + f.numel() * 8
+    mc_bytes = G ** 3 * 4 + v.numel() * v.element_size() + f.numel() * 8    # grid read once + outputs
     up_bytes = ((R + 1) // 2) ** 3 * 4 + R ** 3 * 4      # last-level upsample
     ms_up, _ = timed(lambda: ops.grid_upsample(torch.zeros(((R + 1) // 2,) * 3, device=dev), None, 0.5, want_mask=False))
     res_out[f"mcube_res_{mc}"] = {
