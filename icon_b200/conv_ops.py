@@ -2,6 +2,8 @@
 
 Each function mirrors the torch call it replaces in the reference (cited in encoders.py) and
 enqueues hand-written kernels on the current stream; NCHW fp32, no autograd (inference path)."""
+import weakref
+
 import torch
 
 from . import _C
@@ -26,10 +28,12 @@ def _c(t):
 
 def _pack_tc(w, transposed, n_tile):
     """torch conv weight -> device blob of K-major SWIZZLE_128B fp16 hi/lo tiles (include/icon_b200.h)."""
-    key = (w.data_ptr(), w._version, tuple(w.shape), transposed, n_tile, str(w.device))
+    # keyed on the weight OBJECT (validated through a weak reference: a dead tensor's id / address can be reused
+    # by another model's weights) plus its storage address and version (in-place updates, .to())
+    key = (id(w), w.data_ptr(), w._version, transposed, n_tile)
     hit = _PACK_CACHE.get(key)
-    if hit is not None:
-        return hit
+    if hit is not None and hit[0]() is w:
+        return hit[1]
     wd = w.detach().float()
     if transposed:                                   # [Cin, Cout, KH, KW] -> [Cout, taps*Cin]
         w2 = wd.permute(1, 2, 3, 0).reshape(wd.shape[1], -1)
@@ -54,7 +58,7 @@ def _pack_tc(w, transposed, n_tile):
     blob = torch.stack([tiles(hi), tiles(lo)], dim=2).contiguous().view(torch.uint8).reshape(-1)
     if len(_PACK_CACHE) > 256:
         _PACK_CACHE.clear()
-    _PACK_CACHE[key] = blob
+    _PACK_CACHE[key] = (weakref.ref(w), blob)
     return blob
 
 

@@ -25,6 +25,29 @@ def _tensor_key(*tensors):
     return tuple((t.data_ptr(), t._version, tuple(t.shape), str(t.device)) for t in tensors)
 
 
+class _SourceCache:
+    """A value derived from some input tensors, valid while those very tensor OBJECTS are unchanged.
+
+    The sources are held strongly, so their storage cannot be freed and handed to a different tensor with the
+    same address while the entry lives (a (data_ptr, _version) key alone would then go stale silently)."""
+
+    def __init__(self):
+        self.src, self.versions, self.value = None, None, None
+
+    def get(self, tensors):
+        if self.src is None or len(tensors) != len(self.src):
+            return None
+        same = all(a is b for a, b in zip(tensors, self.src))
+        return self.value if same and tuple(t._version for t in tensors) == self.versions else None
+
+    def put(self, tensors, value):
+        self.src, self.versions, self.value = tuple(tensors), tuple(t._version for t in tensors), value
+        return value
+
+    def clear(self):
+        self.src, self.versions, self.value = None, None, None
+
+
 def init_net(net, init_gain=0.02):
     """lib/net/net_util.py:73-126 with the defaults every caller uses (xavier-normal, gain .02)."""
     def init_func(m):
@@ -180,10 +203,9 @@ class HGPIFuNet(BasePIFuNet):
                 raise NotImplementedError(f"Backbone {self.opt.gtype} is unimplemented")
         self.normal_filter = NormalNet(cfg)
         init_net(self)
-        self._body = None
-        self._body_key = None
-        self._vol_feat = None
-        self._vol_key = None
+        self._body_cache = _SourceCache()     # prepared SmplBody of the current subject
+        self._vol_cache = _SourceCache()      # pamir: encoded semantic volume of the current subject
+        self._vol_feat = None                 # pamir: volume feature handed in directly ('vol' / 'vol_feat')
 
     def set_smpl_constants(self, smpl_vertex_code, smpl_face_code, smpl_faces, smpl_tetras, batch_size=1):
         """What the reference's constructor does with read_smpl_constants() (HGPIFuNet.py:107-118)."""
@@ -192,22 +214,22 @@ class HGPIFuNet(BasePIFuNet):
 
     def _pamir_volume_feature(self):
         """HGPIFuNet.py:314-325: strip the padding, voxelise, encode.  The reference redoes this on every query
-        call; the result only depends on the subject, so it is cached on (data_ptr, _version) of voxel_verts."""
+        call; the result only depends on the subject, so it is cached on the identity and version of the voxel_* tensors."""
         d = self.smpl_feat_dict or {}
         if "voxel_verts" not in d or self.voxelization is None:
             return None
         vv, vf = d["voxel_verts"], d["voxel_faces"]
-        key = (vv.data_ptr(), vv._version, vf.data_ptr(), vf._version)
-        if self._vol_key != key:
+        src = (vv, vf, d["pad_v_num"], d["pad_f_num"])
+        feat = self._vol_cache.get(src)
+        if feat is None:
             pv, pf = int(d["pad_v_num"][0]), int(d["pad_f_num"][0])
             verts = vv[:, :-pv, :] if pv > 0 else vv
             tets = vf[:, :-pf, :] if pf > 0 else vf
             self.voxelization.device = verts.device
             self.voxelization.update_param(batch_size=tets.shape[0], smpl_tetra=tets[0])
             vol = self.voxelization(verts)
-            self._vol_feat = self.ve(vol, intermediate_output=False)[-1]
-            self._vol_key = key
-        return self._vol_feat
+            feat = self._vol_cache.put(src, self.ve(vol, intermediate_output=False)[-1])
+        return feat
 
     # ------------------------------------------------------------------ filter
     def get_normal(self, in_tensor_dict):
@@ -253,7 +275,8 @@ class HGPIFuNet(BasePIFuNet):
             self.smpl_feat_dict = {k: in_tensor_dict[k] for k in self.icon_keys}
         elif self.prior_type == "pamir":
             self.smpl_feat_dict = {k: in_tensor_dict[k] for k in self.pamir_keys if k in in_tensor_dict}
-            self._vol_feat, self._vol_key = None, None
+            self._vol_feat = None
+            self._vol_cache.clear()
             if "vol_feat" in in_tensor_dict:      # pre-encoded volume feature
                 self._vol_feat = in_tensor_dict["vol_feat"]
             elif "vol" in in_tensor_dict:         # semantic volume [1,3,128,128,128] -> VolumeEncoder, once per subject
@@ -269,13 +292,13 @@ class HGPIFuNet(BasePIFuNet):
         if d is None:
             raise RuntimeError("HGPIFuNet.query (icon prior) needs filter() first: smpl_feat_dict is empty")
         ts = [d[k] for k in self.icon_keys]
-        key = _tensor_key(*ts)
-        if self._body is None or key != self._body_key:
+        body = self._body_cache.get(ts)
+        if body is None:
             if d["smpl_verts"].shape[0] != 1:
                 raise NotImplementedError("B=1 on the inference path")
-            self._body = ops.SmplBody(d["smpl_verts"], d["smpl_faces"], d["smpl_cmap"], d["smpl_vis"])
-            self._body_key = key
-        return self._body
+            body = self._body_cache.put(ts, ops.SmplBody(d["smpl_verts"], d["smpl_faces"], d["smpl_cmap"],
+                                                         d["smpl_vis"]))
+        return body
 
     def query(self, features, points, calibs, transforms=None, regressor=None):
         """HGPIFuNet.py:268-367.  points [1,3,N], calibs [1,4,4] -> [preds [1,1,N]]."""
@@ -292,7 +315,7 @@ class HGPIFuNet(BasePIFuNet):
         body = self._prepared_body() if self.prior_type == "icon" else None
         vol = None
         if self.prior_type == "pamir":
-            vol = self._vol_feat if self._vol_feat is not None and self._vol_key is None else self._pamir_volume_feature()
+            vol = self._vol_feat if self._vol_feat is not None else self._pamir_volume_feature()
             if vol is None:
                 raise RuntimeError("pamir prior: filter() needs voxel_verts / voxel_faces / pad_v_num / pad_f_num "
                                    "(plus SMPL constants: <root>/tedra_data or set_smpl_constants()), or a semantic "

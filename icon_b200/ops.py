@@ -345,3 +345,20 @@ def voxelize(verts, n_surface, codes, tets, res, sigma):
     check(lib.icon_voxelize(_p(v), v.shape[0], int(n_surface), _p(c), _p(t), t.shape[0], int(res), float(sigma),
                             _p(out), _p(ws), nbytes, _stream()), "icon_voxelize")
     return out
+
+
+# --------------------------------------------------------------------------- vertex visibility
+def visibility(xyz, faces, image_size=4096):
+    """xyz [V,3] f32 screen-space vertices ((cat(xy, -z) + 1) / 2), faces [F,3] int64 -> vis [V] f32 (0/1), CUDA;
+    include/icon_b200.h: icon_visibility."""
+    _need_cuda(xyz)
+    v = xyz.detach().float().contiguous()
+    f = faces.detach().to(device=v.device, dtype=torch.int64).contiguous()
+    if v.dim() != 2 or v.shape[1] != 3 or f.dim() != 2 or f.shape[1] != 3:
+        raise _C.IconError(f"visibility: xyz {tuple(v.shape)}, faces {tuple(f.shape)}")
+    vis = torch.empty(v.shape[0], dtype=torch.float32, device=v.device)
+    nbytes = lib.icon_visibility_workspace_bytes(int(image_size))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=v.device)
+    check(lib.icon_visibility(_p(v), v.shape[0], _p(f), f.shape[0], int(image_size), _p(vis), _p(ws), nbytes,
+                              _stream()), "icon_visibility")
+    return vis

@@ -186,6 +186,15 @@ size_t icon_voxelize_workspace_bytes(int res);
 int icon_voxelize(const float *verts, int NV, int NVsurf, const float *codes, const int32_t *tets, int NT,
                   int res, float sigma, float *out, void *ws, size_t ws_bytes, icon_stream_t stream);
 
+/* ------------------------------------------------------------------ vertex visibility (producer of smpl_vis)
+ * Replaces get_visibility (lib/dataset/mesh_util.py:280-316): z-buffer rasterisation of the body at
+ * image_size^2 (4096 in the reference) with pytorch3d's conventions (csrc/visibility.cu header; parity unpinned),
+ * vis[v] = 1 for the vertices of every face that owns a pixel (plus the last face's, as faces[-1] does upstream).
+ * xyz [V,3] f32 = (cat(xy, -z) + 1) / 2 as the reference builds it, faces [F,3] i64, vis [V] f32. */
+size_t icon_visibility_workspace_bytes(int image_size);
+int icon_visibility(const float *xyz, int V, const int64_t *faces, int F, int image_size, float *vis,
+                    void *ws, size_t ws_bytes, icon_stream_t stream);
+
 /* ------------------------------------------------------------------ encoder operators (NCHW fp32)
  * Replace the cuDNN / torch calls inside HGFilter (lib/net/HGFilters.py:161-197, ConvBlock
  * lib/net/net_util.py:258-280), GlobalGenerator / ResnetBlock (lib/net/FBNet.py:216-319) and

@@ -32,7 +32,9 @@ def test_library_exports_every_declared_symbol(built_lib):
     # size queries are host-only and must work without a GPU
     assert _C.lib.icon_smpl_workspace_bytes(6890, 13776) > 13776 * 64
     assert _C.lib.icon_query_workspace_bytes(1 << 20, 13776, 0) > (1 << 20) * 32
-    assert _C.lib.icon_mc_workspace_bytes(257, 1) >= 258 ** 3 * 10
+    assert _C.lib.icon_mc_workspace_bytes(257, 1) >= 258 ** 3 * 6        # voff i32 + flags + case per voxel
+    assert _C.lib.icon_voxelize_workspace_bytes(128) >= 128 ** 3
+    assert _C.lib.icon_visibility_workspace_bytes(4096) >= 4096 * 4096 * 8
 
 
 def test_ops_refuse_cpu_tensors(built_lib):
@@ -153,3 +155,22 @@ def test_display_preview_runs_on_cpu_tensor():
     img = eng.display(occ)
     assert img.shape == (33, 4 * 33, 3) and img.dtype == np.uint8
     assert (img != 255).any()
+
+
+def test_source_cache_is_keyed_on_tensor_identity_and_version():
+    """A (data_ptr, _version) key can go stale when a freed tensor's address is reused; the caches of the prepared
+    body / pamir volume hold their sources and compare identity + version instead."""
+    import torch
+    from icon_b200.net import _SourceCache
+    c = _SourceCache()
+    a, b = torch.zeros(4), torch.zeros(3)
+    assert c.get([a, b]) is None
+    c.put([a, b], "value")
+    assert c.get([a, b]) == "value"
+    assert c.get([a.clone(), b]) is None          # equal content, other object
+    a.add_(1)                                     # in-place update bumps the version
+    assert c.get([a, b]) is None
+    c.put([a, b], "new")
+    assert c.get([a, b]) == "new"
+    c.clear()
+    assert c.get([a, b]) is None
