@@ -419,7 +419,7 @@ __global__ void __launch_bounds__(256) k_sdf_brute(const float *__restrict__ pts
 }
 
 // points-per-warp policy of k_sdf_warp (see its header comment); icon_set_sdf_policy() overrides it for tuning
-static int64_t g_sdf_ppw32_from = 1300000, g_sdf_ppw8_from = 300000;
+static int64_t g_sdf_ppw32_from = 6000000, g_sdf_ppw8_from = 300000;
 static int g_sdf_ppw_force = 0;
 
 // ---------------------------------------------------------------- host-side pipeline pieces
@@ -480,9 +480,11 @@ int run_sdf(const float *points, int64_t sc, int64_t sn, int64_t N, const float 
         attr_set = true;
     }
     profile_mark(1, stream);
-    // the kernel needs >= ~50k warps to hide the latency of its tree walk, so the fewer points a call has the fewer
-    // of them a warp carries.  Measured (profiles/r1c_summary.md): 36k / 167k points -> PPW 1 wins, 826k -> PPW 8,
-    // 2.1M (dense 128^3) and up -> PPW 32
+    // the kernel needs many warps in flight to hide the latency of its tree walk, so the fewer points a call has the
+    // fewer of them a warp carries.  The thresholds are tuned on the engine's sparse refinement sets (36k / 167k
+    // points -> PPW 1, 826k .. ~5M -> PPW 8: 3.6 ms of engine time per image instead of 6.6 ms with PPW 32) and the
+    // dense 256^3 lattice (PPW 32).  A DENSE mid-sized call would prefer PPW 32 (2.1M-point lattice: 1.7 vs 2.4 ms);
+    // the point count alone cannot tell the two apart -- callers that know can pin it (icon_set_sdf_policy).
     int ppw = N >= g_sdf_ppw32_from ? 32 : (N >= g_sdf_ppw8_from ? 8 : 1);
     if (g_sdf_ppw_force) ppw = g_sdf_ppw_force;
     const int wpb = SW_T / 32;
