@@ -53,7 +53,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"],
+                                          "-i", str(self.index), "-lms", "25"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -226,7 +226,6 @@ def main():
     barrier()
     ms = e0.elapsed_time(e1)
     launches = _C.launch_count() - l0
-    clocks = sampler.stop() if rank == 0 else None
     checksum = float(out.double().sum().item())
 
     # ---- timed region 2: end to end through query_func with HOST buffers.  Every step copies its points
@@ -269,6 +268,7 @@ def main():
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None      # sampled under load through both timed regions
 
     # ---- per-stage timing of the dominant kernels (CUDA events inside the library, same stream)
     _C.lib.icon_profile_enable(1)

@@ -10,6 +10,8 @@ state_dict keys and shapes, and forwards that run the hand-written conv kernels
 import torch
 import torch.nn as nn
 
+from .graphs import GraphedForward
+
 
 def _conv_ops():
     from . import conv_ops        # imported lazily: needs the CUDA library
@@ -112,6 +114,11 @@ class HGFilter(nn.Module):
                 self.add_module("al" + str(hg_module), nn.Conv2d(opt.hourglass_dim, 256, kernel_size=1, stride=1, padding=0))
 
     def forward(self, x):
+        if not hasattr(self, "_graphed"):
+            object.__setattr__(self, "_graphed", GraphedForward(self, "_forward_eager"))
+        return self._graphed(x, extra=_conv_ops()._IMPL)
+
+    def _forward_eager(self, x):
         C = _conv_ops()
         with torch.no_grad():
             x = C.group_norm(C.conv2d(x, self.conv1), self.bn1, relu=True)
@@ -180,6 +187,11 @@ class GlobalGenerator(nn.Module):
         self.model = nn.Sequential(*model)
 
     def forward(self, x):
+        if not hasattr(self, "_graphed"):
+            object.__setattr__(self, "_graphed", GraphedForward(self, "_forward_eager"))
+        return self._graphed(x, extra=_conv_ops()._IMPL)
+
+    def _forward_eager(self, x):
         C = _conv_ops()
         m = self.model
         with torch.no_grad():

@@ -1,0 +1,80 @@
+"""CUDA-graph replay of the fixed-shape encoder forwards.
+
+One filter() is ~450 kernel launches of 5-50 us each; issued one by one from Python the launch gaps cost several
+milliseconds per image, and NormalNet runs 100 times per image in the reference's SMPL-fitting loop
+(apps/infer.py:168-210).  `GraphedForward` runs a module's tensor -> tensor(s) function eagerly the first time a
+(shape, weights) combination is seen (which also fills the packed-weight caches), captures it into a
+`torch.cuda.CUDAGraph` the second time and replays it afterwards.  Inputs are copied into the graph's static input
+buffer and results are returned as fresh clones, so callers see ordinary tensors.
+
+The key carries the identity and version of every parameter / buffer of the module: loading a checkpoint or moving
+the module invalidates the captured graphs (they hold the old packed-weight pointers).
+"""
+import os
+
+import torch
+
+_ENABLED = os.environ.get("ICON_B200_CUDA_GRAPHS", "1") != "0"
+MAX_GRAPHS_PER_MODULE = 4
+
+
+def enable(flag=True):
+    """Process-wide switch (also: environment ICON_B200_CUDA_GRAPHS=0)."""
+    global _ENABLED
+    _ENABLED = bool(flag)
+
+
+def enabled():
+    return _ENABLED
+
+
+class GraphedForward:
+    def __init__(self, module, method):
+        self.module, self.method = module, method
+        self.entries = {}            # key -> None (seen once, eager) | (graph, static_in, static_out)
+        self.disabled = False
+        self.replays = 0
+
+    def fn(self, x):
+        return getattr(self.module, self.method)(x)
+
+    def __deepcopy__(self, memo):     # graphs are not copied: the copy captures its own
+        import copy
+        return GraphedForward(copy.deepcopy(self.module, memo), self.method)
+
+    def _key(self, x, extra):
+        m = self.module
+        weights = tuple((t.data_ptr(), t._version) for t in list(m.parameters()) + list(m.buffers()))
+        return (tuple(x.shape), x.dtype, str(x.device), extra, weights)
+
+    def __call__(self, x, extra=None):
+        usable = (_ENABLED and not self.disabled and x.is_cuda and not self.module.training
+                  and not torch.cuda.is_current_stream_capturing())
+        if not usable:
+            return self.fn(x)
+        key = self._key(x, extra)
+        if key not in self.entries:
+            if len(self.entries) >= MAX_GRAPHS_PER_MODULE:
+                self.entries.clear()
+            self.entries[key] = None
+            return self.fn(x)                                   # first sight: eager (fills the weight-pack caches)
+        ent = self.entries[key]
+        if ent is None:
+            try:
+                static_in = x.detach().clone()
+                torch.cuda.current_stream().synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    static_out = self.fn(static_in)
+                ent = self.entries[key] = (graph, static_in, static_out)
+            except Exception:                                   # capture not possible here: stay eager from now on
+                self.disabled = True
+                self.entries.clear()
+                return self.fn(x)
+        graph, static_in, static_out = ent
+        static_in.copy_(x)
+        graph.replay()
+        self.replays += 1
+        if isinstance(static_out, (list, tuple)):
+            return type(static_out)(t.clone() for t in static_out)
+        return static_out.clone()

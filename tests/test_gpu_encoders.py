@@ -177,3 +177,38 @@ def test_filter_icon_filter_config_shapes_and_timing():
     e1.record()
     torch.cuda.synchronize()
     print(f"filter (NormalNet + 2 x HGFilter, 512^2): {e0.elapsed_time(e1):.1f} ms")
+
+
+def test_cuda_graph_replay_equals_eager_and_tracks_weight_updates():
+    """icon_b200/graphs.py: 1st call eager, 2nd captured, later replayed; results bit-identical to eager;
+    an in-place weight update invalidates the captured graph."""
+    dev = _cuda()
+    from icon_b200 import encoders, graphs
+
+    class Opt:
+        norm = "group"; hg_down = "ave_pool"; conv1 = [7, 2, 1, 3]; conv3x3 = [3, 1, 1, 1]
+        num_hourglass = 2; hourglass_dim = 6
+
+    hg = encoders.HGFilter(Opt, 2, 3).to(dev).eval()
+    hg.load_state_dict(S.seeded_like(hg.state_dict(), 21))
+    x1 = torch.randn(1, 3, 128, 128, generator=_g(1)).to(dev)
+    x2 = torch.randn(1, 3, 128, 128, generator=_g(2)).to(dev)
+    graphs.enable(False)
+    try:
+        ref1, ref2 = hg(x1)[-1].clone(), hg(x2)[-1].clone()
+    finally:
+        graphs.enable(True)
+    a = hg(x1)[-1]                   # eager (first sight of this key)
+    b = hg(x2)[-1]                   # captured + replayed
+    c = hg(x1)[-1]                   # replayed
+    assert hg._graphed.replays >= 2 and not hg._graphed.disabled
+    assert torch.equal(a, ref1) and torch.equal(b, ref2) and torch.equal(c, ref1)
+    with torch.no_grad():
+        hg.conv1.weight.mul_(1.5)
+    d = hg(x1)[-1]                   # new key -> eager with the new weights
+    graphs.enable(False)
+    try:
+        ref3 = hg(x1)[-1]
+    finally:
+        graphs.enable(True)
+    assert torch.equal(d, ref3) and not torch.equal(d, ref1)

@@ -71,7 +71,7 @@ eng = Seg3dLossless(query_func=net.query_func, b_min=[[-1.0, 1.0, -1.0]], b_max=
 with torch.no_grad():
     ms_f, feats = timed(lambda: netG.filter(batch), n=3, warm=1)
     ms_e, occ = timed(lambda: eng(opt=cfg, netG=netG, features=feats, proj_matrix=None), n=3, warm=1)
-    entry = {"filter_ms (NormalNet + 2 x HGFilter, FP32 conv kernels)": ms_f, "engine_ms_with_network": ms_e,
+    entry = {"filter_ms (NormalNet + 2 x HGFilter)": ms_f, "engine_ms_with_network": ms_e,
              "query_points_per_call": eng.last_query_counts}
     if occ is not None:
         ms_x, (vv, ff) = timed(lambda: eng.export_mesh(occ), n=3, warm=1)
