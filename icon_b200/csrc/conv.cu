@@ -247,22 +247,44 @@ __global__ void __launch_bounds__(256) k_norm_stats(const float *__restrict__ x,
         atomicAdd(&stats[2 * gi + 1], dq);
     }
 }
-__global__ void k_norm_apply(const float *__restrict__ x, const double *__restrict__ stats, const float *__restrict__ gamma,
-                             const float *__restrict__ beta, const float *__restrict__ res, float *__restrict__ y, int C,
-                             int HW, int groups, float eps, int relu, int64_t total) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const int c = (int)((i / HW) % C), n = (int)(i / ((int64_t)HW * C)), cpg = C / groups;
-    const int gi = n * groups + c / cpg;
-    const double cnt = (double)cpg * HW;
+// sums -> (mean, rstd) per group, in place and in double as before; done once per group instead of once per element
+__global__ void k_norm_finalize(double *__restrict__ stats, int ng, double cnt, float eps) {
+    const int gi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gi >= ng) return;
     const double mean = stats[2 * gi] / cnt;
     const double var = fmax(stats[2 * gi + 1] / cnt - mean * mean, 0.0);
-    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
-    float o = (x[i] - (float)mean) * rstd;
-    if (gamma) o = fmaf(o, __ldg(gamma + c), __ldg(beta + c));
-    if (res) o += res[i];
-    if (relu) o = fmaxf(o, 0.f);
-    y[i] = o;
+    stats[2 * gi] = (double)(float)mean;
+    stats[2 * gi + 1] = (double)(float)(1.0 / sqrt(var + (double)eps));
+}
+
+// one (n, c) plane per blockIdx.x, 1024-element segments along blockIdx.y: the group statistics and the affine
+// pair are block-uniform, the element loop is a float4 stream
+__global__ void __launch_bounds__(256) k_norm_apply(const float *__restrict__ x, const double *__restrict__ stats,
+                                                    const float *__restrict__ gamma, const float *__restrict__ beta,
+                                                    const float *__restrict__ res, float *__restrict__ y, int C, int HW,
+                                                    int groups, int relu) {
+    const int plane = blockIdx.x, c = plane % C, n = plane / C;
+    const int gi = n * groups + c / (C / groups);
+    const float mean = (float)stats[2 * gi], rstd = (float)stats[2 * gi + 1];
+    const bool affine = gamma != nullptr;
+    const float g = affine ? __ldg(gamma + c) : 1.f, bt = affine ? __ldg(beta + c) : 0.f;
+    const size_t base = (size_t)plane * HW;
+    auto f = [&](float v, float r) {
+        float o = (v - mean) * rstd;
+        if (affine) o = fmaf(o, g, bt);
+        o += r;
+        return relu ? fmaxf(o, 0.f) : o;
+    };
+    const int i0 = (blockIdx.y * 256 + threadIdx.x) * 4;
+    if (i0 >= HW) return;
+    if ((HW & 3) == 0) {
+        const float4 v = *reinterpret_cast<const float4 *>(x + base + i0);
+        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (res) r = *reinterpret_cast<const float4 *>(res + base + i0);
+        *reinterpret_cast<float4 *>(y + base + i0) = make_float4(f(v.x, r.x), f(v.y, r.y), f(v.z, r.z), f(v.w, r.w));
+    } else {
+        for (int i = i0; i < min(i0 + 4, HW); ++i) y[base + i] = f(x[base + i], res ? res[base + i] : 0.f);
+    }
 }
 
 // ---------------------------------------------------------------- pooling / resampling / joins
@@ -401,9 +423,10 @@ extern "C" int icon_group_norm(const float *x, const float *gamma, const float *
         ICON_CUDA(cudaMemsetAsync(stats_ws, 0, sizeof(double) * 2 * ng, stream));
         k_norm_stats<<<ng * slices, 256, 0, stream>>>(x, C, HW, groups, slices, (double *)stats_ws);
         ICON_LAUNCHED();
-        const int64_t total = (int64_t)N * C * HW;
-        k_norm_apply<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(x, (const double *)stats_ws, gamma, beta, res, y, C,
-                                                                          HW, groups, eps, relu, total);
+        k_norm_finalize<<<(ng + 127) / 128, 128, 0, stream>>>((double *)stats_ws, ng, (double)cnt, eps);
+        ICON_LAUNCHED();
+        k_norm_apply<<<dim3((unsigned)(N * C), (unsigned)((HW + 1023) / 1024)), 256, 0, stream>>>(
+            x, (const double *)stats_ws, gamma, beta, res, y, C, HW, groups, relu);
     } else {
         k_group_norm<<<ng, 512, 0, stream>>>(x, gamma, beta, res, y, C, HW, groups, eps, relu);
     }
