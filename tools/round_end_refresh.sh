@@ -1,3 +1,5 @@
+# Round-end refresh on the GPU box: full GPU test suite, smoke(), bench line, ncu launch list, engine/MC timings.
+# Usage: gpurun --timeout 1000 -- bash tools/round_end_refresh.sh ; then copy gpurun_out/* into profiles/.
 mkdir -p gpurun_out
 timeout -k 5 300 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu_r1c.log 2>&1; tail -3 gpurun_out/pytest_gpu_r1c.log
 timeout -k 5 60 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
