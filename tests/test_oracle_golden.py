@@ -116,3 +116,37 @@ def test_outlier_cmap_rule_is_order_dependent():
             k += 1
         else:
             assert torch.equal(c2[0, i], cmap[0, i])
+
+
+def test_sdf_oracle_tie_rule_lowest_face_index():
+    """kaolin's brute-force scan keeps the first strict minimum, i.e. the LOWEST face index on exact ties
+    (SURVEY 8c).  Outside a tetrahedron most points are nearest to an edge or a vertex, where the incident faces
+    tie exactly; per-face distances from single-face meshes say which faces tie."""
+    v = np.array([[0.0, 0.0, 0.5], [0.5, 0.0, -0.25], [-0.25, 0.4, -0.25], [-0.25, -0.4, -0.25]], np.float32)
+    tet = np.array([[0, 1, 2], [0, 2, 3], [0, 3, 1], [1, 3, 2]], np.int64)
+    g = torch.Generator().manual_seed(4)
+    pts = torch.rand(1, 2000, 3, generator=g) * 2 - 1
+    cm = np.zeros_like(v); vi = np.ones((4, 1), np.float32)
+
+    def run(faces):
+        out = OQ.cal_sdf_batch_c(torch.from_numpy(v)[None], torch.from_numpy(faces)[None], torch.from_numpy(cm)[None],
+                                 torch.from_numpy(vi)[None], pts, return_face=True)
+        return out[0][0, :, 0].abs().numpy(), out[4].numpy()
+
+    D = np.stack([run(tet[k:k + 1])[0] for k in range(4)])            # [4, N] |sdf| to each face alone
+    dist0, face0 = run(tet)
+    assert np.array_equal(dist0, D.min(0))
+    assert np.array_equal(D[face0, np.arange(D.shape[1])], D.min(0))   # the winner attains the minimum
+    near_ties = (D == D.min(0, keepdims=True)).sum(0) > 1             # equal after sqrt: edge / vertex regions
+    assert near_ties.mean() > 0.2
+    for k in range(4):
+        # a bit-identical twin of face k placed FIRST takes over every point face k used to win (lower index) ...
+        _, face1 = run(np.concatenate([tet[k:k + 1], tet], 0))
+        won = face0 == k
+        assert won.any() and (face1[won] == 0).all()
+        # ... and may take a point from another face only where that face tied with k
+        moved = (~won) & (face1 != face0 + 1)
+        assert (face1[moved] == 0).all() and (D[k, moved] == D.min(0)[moved]).all()
+        # placed LAST it never wins: only a strictly smaller distance replaces the current best
+        _, face2 = run(np.concatenate([tet, tet[k:k + 1]], 0))
+        assert np.array_equal(face2, face0)
