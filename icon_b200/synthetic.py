@@ -146,3 +146,39 @@ def tet_body(rings=82, segs=84, seed=0, extent=(0.22, 0.42, 0.12)):
     lo, hi = verts.min(0, keepdims=True), verts.max(0, keepdims=True)
     code = ((verts - lo) / (hi - lo)).astype(np.float32)
     return allv.astype(np.float32), V, tets, code
+
+
+def encoder_inputs_512(seed=5, size=512):
+    """image / T_normal_F / T_normal_B [1,3,size,size] in [-1,1] with a centred elliptical foreground; everything
+    outside the ellipse is exactly 0 in all three maps (the background NormalNet masks, lib/net/NormalNet.py:93-97)."""
+    g = torch.Generator().manual_seed(seed)
+    a = (torch.arange(size, dtype=torch.float32) + 0.5) / size * 2 - 1
+    yy, xx = torch.meshgrid(a, a, indexing="ij")
+    fg = ((xx / 0.55) ** 2 + (yy / 0.9) ** 2 < 1.0).float()[None, None]
+    out = {}
+    for k in ("image", "T_normal_F", "T_normal_B"):
+        lo = torch.rand(1, 3, size // 8, size // 8, generator=g) * 2 - 1          # smooth part
+        hi = torch.rand(1, 3, size, size, generator=g) * 2 - 1                      # pixel noise
+        smooth = torch.nn.functional.interpolate(lo, size=(size, size), mode="bilinear", align_corners=False)
+        out[k] = ((0.7 * smooth + 0.3 * hi).clamp(-1, 1) * fg).contiguous()
+    return out
+
+
+def adversarial_points(verts, faces, n_each=600, seed=0):
+    """Query points that sit on the decision boundaries of cal_sdf_batch for a given mesh: exactly on vertices, on
+    fp32 edge midpoints and face centroids (distance 0, many equidistant faces), points whose +x ray passes exactly
+    through a vertex or an edge midpoint (same y, z; the parity ray of check_sign), and random points near the
+    surface.  Returns [1, n, 3] float32."""
+    rng = np.random.RandomState(seed)
+    v = verts.astype(np.float32)
+    f = faces.astype(np.int64)
+    vi = rng.randint(len(v), size=n_each)
+    fi = rng.randint(len(f), size=n_each)
+    on_vert = v[vi]
+    mid = ((v[f[fi, 0]] + v[f[fi, 1]]) * np.float32(0.5)).astype(np.float32)
+    cen = ((v[f[fi, 0]] + v[f[fi, 1]] + v[f[fi, 2]]) / np.float32(3.0)).astype(np.float32)
+    ray_v = v[vi].copy(); ray_v[:, 0] -= rng.uniform(0.01, 0.6, n_each).astype(np.float32)
+    ray_e = mid.copy(); ray_e[:, 0] -= rng.uniform(0.01, 0.6, n_each).astype(np.float32)
+    near = (cen + 0.02 * rng.standard_normal(cen.shape)).astype(np.float32)
+    pts = np.concatenate([on_vert, mid, cen, ray_v, ray_e, near], 0).astype(np.float32)
+    return torch.from_numpy(pts)[None]

@@ -241,8 +241,13 @@ def mlp_forward(sd, feature, res_layers=(2, 3, 4), last_op=None, dtype=torch.flo
 # ----------------------------------------------------------------------------- query
 def query(mlp_sd, features, points, calibs, prior="icon", smpl=None, sdf_clip=0.05,
           smpl_feats=("sdf", "norm", "vis", "cmap"), res_layers=(2, 3, 4), vol_feat=None,
-          return_point_feat=False, mlp_dtype=torch.float32):
+          return_point_feat=False, mlp_dtype=torch.float32, outlier_context=None):
     """HGPIFuNet.query (HGPIFuNet.py:268-367), eval mode, one feature stack.
+
+    outlier_context: None when `points` is the WHOLE call.  To check a subset of a larger call (the cmap
+    overwrite at HGPIFuNet.py:303-304 depends on every outlier of the call), pass (signs_all, rank): signs_all
+    [K] = sign(sdf) of all K outliers of the full call in point order, rank [n] = for each subset point its
+    index among the full call's outliers (ignored where the point is not an outlier).
 
     features: list with one [1,C,H,W] tensor; points [1,3,N]; calibs [1,4,4];
     smpl: dict smpl_verts/smpl_faces/smpl_cmap/smpl_vis (prior 'icon');
@@ -260,9 +265,18 @@ def query(mlp_sd, features, points, calibs, prior="icon", smpl=None, sdf_clip=0.
         smpl_outlier = torch.abs(smpl_sdf).ge(sdf_clip)
         smpl_sdf[smpl_outlier] = torch.sign(smpl_sdf[smpl_outlier])
         feat_lst = [smpl_sdf]
-        if "cmap" in smpl_feats:
+        if "cmap" in smpl_feats and outlier_context is None:
             # HGPIFuNet.py:303-304 -- the order-dependent overwrite
             smpl_cmap[smpl_outlier.repeat(1, 1, 3)] = smpl_sdf[smpl_outlier].repeat(1, 1, 3)
+            feat_lst.append(smpl_cmap)
+        elif "cmap" in smpl_feats:
+            # the same statement seen from a subset of the call: masked positions are enumerated point-major
+            # (3k+c for the k-th outlier's channel c) and the source is the K signs tiled three times
+            signs_all, rank = outlier_context
+            K = signs_all.numel()
+            out_idx = smpl_outlier[0, :, 0].nonzero().reshape(-1)
+            for c in range(3):
+                smpl_cmap[0, out_idx, c] = signs_all[(3 * rank[out_idx] + c) % K].to(smpl_cmap.dtype)
             feat_lst.append(smpl_cmap)
         if "norm" in smpl_feats:
             feat_lst.append(smpl_norm)

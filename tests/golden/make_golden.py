@@ -150,6 +150,39 @@ def main():
         yv = ve(xv, intermediate_output=False)
     enc["ve_x"], enc["ve_y"] = xv.numpy(), yv[-1].numpy()
     np.savez_compressed(os.path.join(HERE, "encoders.npz"), **enc)
+
+    # ---------------------------------------------------------------- encoders at the BASELINE resolution (512 x 512)
+    # Inputs and weights are regenerated from seeds by the tests (icon_b200.synthetic.encoder_inputs_512 /
+    # seeded_like); only outputs are stored: HGFilter in full ([1,6,128,128]), the 512 x 512 normal maps as a
+    # strided subsample (every 4th row / column, phase (1, 2)) plus float64 per-channel sums of the full maps.
+    e5 = {}
+    batch = S.encoder_inputs_512(seed=5)
+    hg.load_state_dict(seeded_state_dict(hg, 21))
+    with torch.no_grad():
+        y = hg(batch["image"])
+    e5["hg_y"] = y[-1].numpy()
+    gg.load_state_dict(seeded_state_dict(gg, 22))
+    with torch.no_grad():
+        y6 = gg(torch.cat([batch["image"], batch["T_normal_F"]], 1))
+    e5["gg_y_sub"] = y6[:, :, 1::4, 2::4].numpy()
+    e5["gg_y_sum"] = y6.double().sum(dim=(0, 2, 3)).numpy()
+
+    import lib.net.NormalNet as RN                   # reference NormalNet.forward (lib/net/NormalNet.py:74-99)
+    RN.VGGLoss = lambda: None                        # training-only perceptual loss (downloads VGG19): not on the path
+
+    class Cfg:
+        class net:
+            in_nml = (("image", 3), ("T_normal_F", 3), ("T_normal_B", 3))
+    nn_ref = RN.NormalNet(Cfg)
+    nn_ref.load_state_dict(seeded_state_dict(nn_ref, 24)); nn_ref.eval()
+    with torch.no_grad():
+        nF, nB = nn_ref(batch)
+    e5["nml_keys"] = np.asarray(sorted(nn_ref.state_dict().keys()))
+    for tag, t in (("F", nF), ("B", nB)):
+        e5[f"nml{tag}_sub"] = t[:, :, 1::4, 2::4].numpy()
+        e5[f"nml{tag}_sum"] = t.double().sum(dim=(0, 2, 3)).numpy()
+        e5[f"nml{tag}_abs"] = t.double().abs().sum(dim=(0, 2, 3)).numpy()
+    np.savez_compressed(os.path.join(HERE, "encoders512.npz"), **e5)
     print("golden fixtures written to", HERE)
 
 

@@ -152,6 +152,88 @@ def test_volume_encoder_matches_reference_module(golden_dir):
     assert np.abs(y[0].cpu().numpy() - g["ve_y"]).max() <= 1e-4
 
 
+@pytest.mark.parametrize("kind,C,hw", [
+    ("group", 512, 64), ("group", 256, 128), ("group", 64, 512), ("group", 128, 256), ("group", 256, 32),
+    ("instance", 64, 512), ("instance", 128, 256), ("instance", 256, 128), ("instance", 512, 64),
+    ("instance", 1024, 32), ("instance", 1024, 8)])
+def test_every_norm_dispatch_path_matches_torch(kind, C, hw):
+    """icon_group_norm picks one of four kernels from (groups x samples, elements per group) -- csrc/conv.cu
+    icon_group_norm; the shapes here are the ones the 512 x 512 encoders produce (plus small ones), so every
+    branch is compared with torch.nn.GroupNorm(32, C) / InstanceNorm2d."""
+    dev = _cuda()
+    from icon_b200 import conv_ops as C_
+    x = torch.randn(1, C, hw, hw, generator=_g(C + hw)) * 1.7 + 0.3
+    x[:, ::3] *= 4.0
+    if kind == "group":
+        m = nn.GroupNorm(32, C)
+        with torch.no_grad():
+            m.weight.copy_(1 + 0.1 * torch.randn(C, generator=_g(3)))
+            m.bias.copy_(0.1 * torch.randn(C, generator=_g(4)))
+            ref = F.relu(m(x))
+        y = C_.group_norm(x.to(dev), m.to(dev), relu=True)
+    else:
+        with torch.no_grad():
+            ref = F.relu(nn.InstanceNorm2d(C, affine=False)(x))
+        y = C_.instance_norm(x.to(dev), relu=True)
+    err = (y.cpu() - ref).abs().max().item()
+    assert err <= 3e-5, (kind, C, hw, err)
+
+
+def _enc512(golden_dir):
+    return np.load(os.path.join(golden_dir, "encoders512.npz")), S.encoder_inputs_512(seed=5)
+
+
+def test_hgfilter_512_matches_reference_module(golden_dir):
+    """HGFilter at the BASELINE resolution (512 x 512 -> [1,6,128,128]) against the reference's own module."""
+    dev = _cuda()
+    from icon_b200 import config
+    from icon_b200.encoders import HGFilter
+    g, batch = _enc512(golden_dir)
+    hg = HGFilter(config.preset("icon-filter").net, 2, 3)
+    hg.load_state_dict(S.seeded_like(hg.state_dict(), 21))
+    hg = hg.to(dev).eval()
+    for _ in range(3):                                   # eager, captured, replayed (icon_b200/graphs.py)
+        y = hg(batch["image"].to(dev))[-1]
+        assert tuple(y.shape) == tuple(g["hg_y"].shape) == (1, 6, 128, 128)
+        err = np.abs(y.cpu().numpy() - g["hg_y"]).max()
+        assert err <= 2e-4 * max(1.0, np.abs(g["hg_y"]).max()), err
+
+
+def test_global_generator_512_matches_reference_module(golden_dir):
+    dev = _cuda()
+    from icon_b200.encoders import GlobalGenerator
+    g, batch = _enc512(golden_dir)
+    gg = GlobalGenerator(6, 3, 64, 4, 9)
+    gg.load_state_dict(S.seeded_like(gg.state_dict(), 22))
+    gg = gg.to(dev).eval()
+    y = gg(torch.cat([batch["image"], batch["T_normal_F"]], 1).to(dev)).cpu()
+    assert tuple(y.shape) == (1, 3, 512, 512)
+    assert np.abs(y[:, :, 1::4, 2::4].numpy() - g["gg_y_sub"]).max() <= 2e-4
+    assert np.abs(y.double().sum(dim=(0, 2, 3)).numpy() - g["gg_y_sum"]).max() <= 2e-4 * 512 * 512 * 0.05
+
+
+def test_normalnet_forward_512_matches_reference_module(golden_dir):
+    """NormalNet.forward end to end (two generators + L2 normalise + background mask, lib/net/NormalNet.py:74-99)."""
+    dev = _cuda()
+    from icon_b200 import config
+    from icon_b200.encoders import NormalNet
+    g, batch = _enc512(golden_dir)
+    nn_ = NormalNet(config.preset("icon-filter"))
+    sd = nn_.state_dict()
+    assert sorted(sd.keys()) == list(g["nml_keys"])
+    nn_.load_state_dict(S.seeded_like(sd, 24))
+    nn_ = nn_.to(dev).eval()
+    with torch.no_grad():
+        nF, nB = nn_({k: v.to(dev) for k, v in batch.items()})
+    bg = (batch["image"].abs().sum(1, keepdim=True) == 0)
+    for tag, t in (("F", nF.cpu()), ("B", nB.cpu())):
+        assert tuple(t.shape) == (1, 3, 512, 512)
+        assert (t[bg.expand_as(t)] == 0).all()                               # masked background is exactly 0
+        assert np.abs(t[:, :, 1::4, 2::4].numpy() - g[f"nml{tag}_sub"]).max() <= 2e-4, tag
+        assert np.abs(t.double().sum(dim=(0, 2, 3)).numpy() - g[f"nml{tag}_sum"]).max() <= 1.0
+        assert np.abs(t.double().abs().sum(dim=(0, 2, 3)).numpy() - g[f"nml{tag}_abs"]).max() <= 1.0
+
+
 def test_filter_icon_filter_config_shapes_and_timing():
     """HGPIFuNet.filter on the BASELINE config (icon-filter, 512x512): NormalNet + 2 x HGFilter."""
     dev = _cuda()

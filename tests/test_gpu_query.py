@@ -89,6 +89,64 @@ def test_sdf_block_bit_exact_vs_oracle(kind, ppw, sdf_policy, mlp_impl):
     assert torch.equal(rec[:, 1:7], ref_rec[:, 1:7]), "cmap / normal not bit-exact"
 
 
+def _scan_body(golden_dir):
+    g = np.load(os.path.join(golden_dir, "scan_body.npz"))
+    v, f = g["verts"], g["faces"].astype(np.int64)
+    cm, vi = S.body_attributes(v, seed=3)
+    return (torch.from_numpy(v)[None], torch.from_numpy(f)[None], torch.from_numpy(cm)[None],
+            torch.from_numpy(vi)[None])
+
+
+@pytest.mark.parametrize("ppw", [0, 1, 8, 32])
+@pytest.mark.parametrize("kind", ["adversarial", "random", "lattice"])
+def test_sdf_block_bit_exact_on_real_scan_body(kind, ppw, sdf_policy, mlp_impl, golden_dir):
+    """tests/golden/scan_body.npz: a body decimated from the reference's THuman2 scan -- non-watertight, 907
+    non-manifold edges, slivers, 8 exactly zero-area faces.  Query points on vertices / edges / faces and with the
+    parity ray passing exactly through vertices and edge midpoints.  Nearest face (lowest-index tie rule), sdf, sign,
+    cmap, normal, visibility must equal the brute-force oracle bit for bit."""
+    if mlp_impl != "tcgen05":
+        pytest.skip("SDF block does not depend on the MLP implementation")
+    dev = _cuda()
+    from icon_b200 import ops
+    sdf_policy(ppw)
+    verts, faces, cmap, vis = _scan_body(golden_dir)
+    if kind == "adversarial":
+        pts = S.adversarial_points(verts[0].numpy(), faces[0].numpy(), n_each=500, seed=1)
+    elif kind == "random":
+        pts = _points(6000, seed=4)
+    else:
+        pts = S.lattice_points(20)
+    body = ops.SmplBody(verts.to(dev), faces.to(dev), cmap.to(dev), vis.to(dev))
+    rec, face = ops.sdf_only(pts.permute(0, 2, 1).to(dev), EYE, body)
+    ref_rec, ref_face = _rec_from_oracle(verts, faces, cmap, vis, pts)
+    rec, face = rec.cpu(), face.cpu()
+    assert torch.equal(face, ref_face), f"nearest-face mismatch on {(face != ref_face).sum().item()} points"
+    assert torch.equal(rec[:, 0], ref_rec[:, 0]), \
+        f"sdf not bit-exact on {(rec[:, 0] != ref_rec[:, 0]).sum().item()} points"
+    assert torch.equal(rec[:, 7], ref_rec[:, 7]), "visibility bit mismatch"
+    assert torch.equal(rec[:, 1:7], ref_rec[:, 1:7]), "cmap / normal not bit-exact"
+
+
+def test_query_func_on_real_scan_body_matches_oracle(mlp_impl, golden_dir):
+    dev = _cuda()
+    from icon_b200 import config, net
+    from oracle import query as OQ
+    verts, faces, cmap, vis = _scan_body(golden_dir)
+    cfg = config.preset("icon-filter")
+    netG = net.HGPIFuNet(cfg).to(dev).eval()
+    sd = S.mlp_state_dict(c0=13, seed=2)
+    netG.if_regressor.load_state_dict(sd)
+    smpl = {"smpl_verts": verts, "smpl_faces": faces, "smpl_cmap": cmap, "smpl_vis": vis}
+    netG.smpl_feat_dict = {k: t.to(dev) for k, t in smpl.items()}
+    feat = S.feature_map(12, 128, seed=2)
+    pts = torch.cat([S.adversarial_points(verts[0].numpy(), faces[0].numpy(), n_each=300, seed=2),
+                     _points(4000, seed=5)], 1)
+    with torch.no_grad():
+        out = net.query_func(cfg, netG, [feat.to(dev)], pts.to(dev)).cpu()
+    ref = OQ.query_func(sd, [feat], pts, prior="icon", smpl=smpl, sdf_clip=0.05)
+    assert (out - ref).abs().max() <= 1e-4
+
+
 @pytest.mark.parametrize("ppw", [1, 8, 32])
 def test_sdf_bricks_equal_bruteforce_kernel(ppw, sdf_policy):
     dev = _cuda()
