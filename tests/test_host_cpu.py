@@ -107,12 +107,9 @@ def test_presets_give_reference_mlp_width(name, c0):
     assert g.if_regressor.last_op is None          # test_mode: no sigmoid (HGPIFuNet.py:133)
 
 
-def test_drop_in_import_paths():
-    from lib.net import HGPIFuNet, NormalNet, VolumeEncoder, BasePIFuNet  # noqa: F401
-    from lib.net.MLP import MLP  # noqa: F401
-    from lib.net.HGFilters import HGFilter  # noqa: F401
-    from lib.common.seg3d_lossless import Seg3dLossless
-    from lib.common.train_util import query_func  # noqa: F401
+def test_engine_constructor_contract():
+    """Seg3dLossless ctor as apps/ICON.py:78-90 calls it (the import-path side is tests/test_overlay_cpu.py)."""
+    from icon_b200.engine import Seg3dLossless
     eng = Seg3dLossless(query_func=None, b_min=[[-1.0, 1.0, -1.0]], b_max=[[1.0, -1.0, 1.0]],
                         resolutions=[33, 65, 129, 257], align_corners=True, faster=True)
     assert set(dict(eng.named_buffers())) >= {"b_min", "b_max", "resolutions"}

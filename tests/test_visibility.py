@@ -79,7 +79,7 @@ def test_visibility_vs_oracle(S_img, rings, segs):
 def test_visibility_quads_and_cpu_inputs():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
-    from lib.dataset.mesh_util import get_visibility
+    from icon_b200.visibility import get_visibility
     from oracle import visibility as OV
     v, f = _two_quads()
     f = _oriented(v, f)
