@@ -44,3 +44,45 @@ def test_gloo_world2_max_and_gather():
     assert m0 == [0, 1, 2] and m1 == [3, 4]
     assert ms0 == ms1 == [11.0, 3.0]                      # max over ranks, element-wise
     assert h0 == h1 == [[0.0, 3.0, 3.0], [1.0, 2.0, 7.0]]  # every rank sees every header, in rank order
+
+
+def _fake_mesh(i):
+    """Deterministic variable-length 'mesh' for image i (image 2 is empty: engine returned None)."""
+    g = torch.Generator().manual_seed(100 + i)
+    nv, nf = (0, 0) if i == 2 else (50 + 17 * i, 90 + 31 * i)
+    dt = torch.float64 if i % 2 else torch.float32          # both export_mesh branches (PyMCubes f64 / kaolin f32)
+    return torch.rand(nv, 3, generator=g, dtype=dt), torch.randint(0, max(nv, 1), (nf, 3), generator=g)
+
+
+def _mesh_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        mine = D.shard_images(5, rank, world)
+        got, nbytes = D.gather_meshes([_fake_mesh(i) for i in mine], mine, torch.device("cpu"))
+        dist.barrier()
+        q.put((rank, {i: (v.clone(), f.clone()) for i, (v, f) in got.items()}, nbytes))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2_mesh_gather_equals_single_process():
+    """Per-image results after the sharded run + gather are identical to producing all images in one process."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_mesh_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=120) for _ in range(2)), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, got0, b0), (_, got1, b1) = res
+    assert got1 == {} and sorted(got0) == [0, 1, 2, 3, 4]
+    for i in range(5):
+        v, f = _fake_mesh(i)
+        assert got0[i][0].dtype == v.dtype and torch.equal(got0[i][0], v) and torch.equal(got0[i][1], f)
+    assert b0 == b1 > 0                                      # bytes received on rank 0 == bytes sent by rank 1
+    single, _ = D.gather_meshes([_fake_mesh(i) for i in range(5)], list(range(5)), torch.device("cpu"))
+    assert sorted(single) == [0, 1, 2, 3, 4]

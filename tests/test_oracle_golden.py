@@ -201,3 +201,23 @@ def test_c_oracle_equals_torch_transcription_on_real_scan_body(golden_dir):
     assert (sdf - sdf_t).abs().max() <= 1e-6
     assert (cmo[0][same] - cm_t[0][same]).abs().max() <= 1e-4
     assert torch.equal(vo[0][same], vis_t[0][same])
+
+
+def test_stock_torch_encoder_restatement_matches_reference_goldens(golden_dir):
+    """tools/torch_encoders.py (stock torch ops on icon_b200's parameter containers = the cuDNN baseline of bench.py)
+    against the outputs of the reference's own HGFilter / GlobalGenerator (tests/golden/encoders.npz, 64 x 64)."""
+    import os
+    import numpy as np
+    from icon_b200 import config, synthetic as S
+    from icon_b200.encoders import GlobalGenerator, HGFilter
+    from tools import torch_encoders as OE
+    g = np.load(os.path.join(golden_dir, "encoders.npz"))
+    hg = HGFilter(config.preset("icon-filter").net, 2, 3)
+    hg.load_state_dict(S.seeded_like(hg.state_dict(), 21)); hg.eval()
+    gg = GlobalGenerator(6, 3, 64, 4, 9)
+    gg.load_state_dict(S.seeded_like(gg.state_dict(), 22)); gg.eval()
+    with torch.no_grad():
+        y = OE.hgfilter(hg, torch.from_numpy(g["hg_x"]))[-1]
+        y6 = OE.global_generator(gg, torch.from_numpy(g["gg_x"]))
+    assert np.abs(y.numpy() - g["hg_y"]).max() <= 1e-5
+    assert np.abs(y6.numpy() - g["gg_y"]).max() <= 1e-5
