@@ -11,14 +11,16 @@ from ._C import check, lib
 from .ops import _need_cuda, _p, _stream
 
 
-_IMPL = "auto"        # "auto": tcgen05 kernel when Cin % 64 == 0, FP32 kernel otherwise; "fp32": always FP32
+# "auto": encoders run the NHWC / TMA path (icon_b200/nhwc.py); single ops here use the NCHW tcgen05 kernel when
+# Cin % 64 == 0 and the FP32 kernel otherwise.  "nchw": the round-1 NCHW path everywhere.  "fp32": always FP32.
+_IMPL = "auto"
 _PACK_CACHE = {}
 NUM_SMS = 148
 
 
 def set_conv_impl(name):
     global _IMPL
-    assert name in ("auto", "fp32")
+    assert name in ("auto", "nchw", "fp32")
     _IMPL = name
 
 
@@ -56,8 +58,9 @@ def _pack_tc(w, transposed, n_tile):
         return t.gather(3, index).permute(0, 2, 1, 3, 4)                 # -> [tile, chunk, row, c16', elem]
 
     blob = torch.stack([tiles(hi), tiles(lo)], dim=2).contiguous().view(torch.uint8).reshape(-1)
-    if len(_PACK_CACHE) > 256:
-        _PACK_CACHE.clear()
+    if len(_PACK_CACHE) > 256:                       # evict only entries whose weight tensor is gone: a live weight's
+        for k in [k for k, v in _PACK_CACHE.items() if v[0]() is None]:     # blob may be baked into a captured CUDA graph
+            del _PACK_CACHE[k]
     _PACK_CACHE[key] = (weakref.ref(w), blob)
     return blob
 
@@ -100,7 +103,7 @@ def conv2d(x, conv, reflect=0, tanh=False, relu=False, residual=None):
     b = _c(conv.bias) if conv.bias is not None else None
     r = _c(residual) if residual is not None else None
     act = 2 if tanh else (1 if relu else 0)
-    if _IMPL == "auto" and Cin % 64 == 0:
+    if _IMPL != "fp32" and Cin % 64 == 0:
         _conv_tc(x, conv.weight, b, r, y, N, Cin, H, W, Cout, KH, KW, stride, pad, 0, 1 if reflect else 0, 0, act)
         return y
     check(lib.icon_conv2d(_p(x), _p(w), _p(b), _p(r), _p(y), N, Cin, H, W, Cout, KH, KW, stride, pad, 0,
@@ -120,7 +123,7 @@ def conv_transpose2d(x, conv):
     OW = (W - 1) * s - 2 * p + KW + op
     y = torch.empty(N, Cout, OH, OW, dtype=torch.float32, device=x.device)
     b = _c(conv.bias) if conv.bias is not None else None
-    if _IMPL == "auto" and Cin % 64 == 0:
+    if _IMPL != "fp32" and Cin % 64 == 0:
         _conv_tc(x, conv.weight, b, None, y, N, Cin, H, W, Cout, KH, KW, s, p, op, 0, 1, 0)
         return y
     check(lib.icon_conv2d(_p(x), _p(w), _p(b), None, _p(y), N, Cin, H, W, Cout, KH, KW, s, p, op, 0, 1, 0, _stream()),

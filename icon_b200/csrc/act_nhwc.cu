@@ -1,0 +1,374 @@
+// NHWC companions of conv_nhwc.cu: everything between two convolutions of the encoders in ONE pass each.
+//
+//   k_norm_finalize   per-(image, channel) sums from the producing kernel's epilogue -> (scale, shift) per channel for
+//                     nn.InstanceNorm2d(affine=False) / nn.GroupNorm(32, C)        (FBNet.py:216-261, net_util.py:258-280)
+//   k_act_nhwc        y = [relu]( x * scale + shift ) [+ residual]  ->  fp16 hi / lo NHWC operand tensors in the layout the
+//                     CONSUMING convolution wants (reflection halo, space-to-depth planes for stride 2, channel padding
+//                     to 64) and / or an fp32 NHWC tensor
+//   k_ew_nhwc         add2 / add3 / 2x2 average pool / bicubic x2 upsample + add (HGFilters.py:49-79), each also
+//                     accumulating the statistics of its result for the GroupNorm that reads it next
+//   k_nchw_to_nhwc / k_nhwc_to_nchw   layout adaptors at the ends of an encoder (+ statistics)
+//   k_conv7_head      the 64 -> 3 channel 7 x 7 reflect-padded output convolution + tanh of the pix2pixHD generator
+//                     (FBNet.py:258-261): N = 3 cannot use a 128 x N tensor-core tile, FP32 FMA from NHWC
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace icon {
+
+// ---------------------------------------------------------------------------------------- statistics -> scale / shift
+// stats [N][C][2] doubles (sum, sum of squares over `count` pixels).  groups == 0: per channel (instance norm).
+__global__ void k_norm_finalize(const double *__restrict__ stats, const float *__restrict__ gamma,
+                                const float *__restrict__ beta, float2 *__restrict__ ss, int N, int C, int groups,
+                                double count, float eps) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N * C) return;
+    const int n = i / C, c = i % C;
+    double s = 0.0, q = 0.0, cnt = count;
+    if (groups <= 0) {
+        s = stats[(size_t)i * 2]; q = stats[(size_t)i * 2 + 1];
+    } else {
+        const int cg = C / groups, g0 = (c / cg) * cg;
+        for (int k = 0; k < cg; ++k) {
+            s += stats[((size_t)n * C + g0 + k) * 2];
+            q += stats[((size_t)n * C + g0 + k) * 2 + 1];
+        }
+        cnt = count * cg;
+    }
+    const double mean = s / cnt;
+    double var = q / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+    ss[i] = make_float2(rstd * g, b - (float)mean * rstd * g);
+}
+
+// ---------------------------------------------------------------------------------------- normalise + split
+struct ActParams {
+    const float *x;          // fp32 NHWC [N][H][W][Cs_in], channels [ci_off, ci_off + C)
+    const float2 *ss;        // [N][C] scale / shift or null (identity)
+    const float *res;        // fp32 NHWC [N][H][W][C] or null: added AFTER the activation
+    __half *hi, *lo;         // [N * planes][Hp][Wp][Cp] or null
+    float *f32;              // fp32 NHWC [N][H][W][C] or null
+    int N, H, W, C, Cs_in, ci_off, Cp;
+    int P;                   // halo (reflection) around the image in hi / lo; 0 with s2d
+    int s2d;                 // 1: 4 parity planes of (H/2, W/2) -- plane = (y & 1) * 2 + (x & 1)
+    int relu;
+};
+
+// one thread = one (destination pixel, 8-channel group)
+__global__ void k_act_nhwc(const __grid_constant__ ActParams p) {
+    const int groups = p.Cp / 8;
+    const int Hd = p.s2d ? p.H : p.H + 2 * p.P, Wd = p.s2d ? p.W : p.W + 2 * p.P;
+    const int64_t total = (int64_t)p.N * Hd * Wd * groups;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int g = (int)(i % groups);
+    int64_t r = i / groups;
+    const int dx = (int)(r % Wd); r /= Wd;
+    const int dy = (int)(r % Hd);
+    const int n = (int)(r / Hd);
+    int sy = dy - p.P, sx = dx - p.P;                          // source pixel (reflection for the halo)
+    const bool interior = sy >= 0 && sy < p.H && sx >= 0 && sx < p.W;
+    sy = sy < 0 ? -sy : (sy >= p.H ? 2 * p.H - 2 - sy : sy);
+    sx = sx < 0 ? -sx : (sx >= p.W ? 2 * p.W - 2 - sx : sx);
+    const int c0 = g * 8;
+    float v[8];
+    const size_t spix = ((size_t)n * p.H + sy) * p.W + sx;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int c = c0 + k;
+        float y = 0.f;
+        if (c < p.C) {
+            y = p.x[spix * p.Cs_in + p.ci_off + c];
+            if (p.ss) { const float2 s = __ldg(p.ss + (size_t)n * p.C + c); y = fmaf(y, s.x, s.y); }
+            if (p.relu) y = fmaxf(y, 0.f);
+            if (p.res) y += p.res[spix * p.C + c];
+        }
+        v[k] = y;
+    }
+    if (p.f32 && interior) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (c0 + k < p.C) p.f32[spix * p.C + c0 + k] = v[k];
+    }
+    if (p.hi) {
+        size_t d;
+        if (p.s2d) {
+            const int plane = (dy & 1) * 2 + (dx & 1);
+            d = ((((size_t)n * 4 + plane) * (p.H / 2) + (dy >> 1)) * (p.W / 2) + (dx >> 1)) * p.Cp + c0;
+        } else {
+            d = (((size_t)n * Hd + dy) * Wd + dx) * p.Cp + c0;
+        }
+        __align__(16) __half h[8], l[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            h[k] = __float2half_rn(v[k]);
+            l[k] = __float2half_rn(v[k] - __half2float(h[k]));
+        }
+        *reinterpret_cast<uint4 *>(p.hi + d) = *reinterpret_cast<const uint4 *>(h);
+        *reinterpret_cast<uint4 *>(p.lo + d) = *reinterpret_cast<const uint4 *>(l);
+    }
+}
+
+// ---------------------------------------------------------------------------------------- elementwise + statistics
+struct EwParams {
+    const float *a, *b, *c;  // fp32 NHWC
+    float *y;
+    double *stats;           // [N][C][2] or null
+    int N, H, W, C;          // OUTPUT dims
+    int mode;                // 0: a + b (+ c)   1: avg_pool2(a) (a is [N][2H][2W][C])   2: b + bicubic_up2(a) (a is [N][H/2][W/2][C])
+};
+
+__device__ __forceinline__ void cubic_w4(float t, float (&w)[4]) {     // torch upsample_bicubic2d, A = -0.75
+    const float A = -0.75f;
+    float x;
+    x = t + 1.f; w[0] = ((A * x - 5.f * A) * x + 8.f * A) * x - 4.f * A;
+    x = t;       w[1] = ((A + 2.f) * x - (A + 3.f)) * x * x + 1.f;
+    x = 1.f - t; w[2] = ((A + 2.f) * x - (A + 3.f)) * x * x + 1.f;
+    x = 2.f - t; w[3] = ((A * x - 5.f * A) * x + 8.f * A) * x - 4.f * A;
+}
+
+constexpr int EW_PIX = 256;          // pixels per block
+// grid (ceil(H*W / EW_PIX), N), 256 threads: thread = (channel quad, pixel row); C % 4 == 0, C / 4 divides 256
+__global__ void __launch_bounds__(256) k_ew_nhwc(const __grid_constant__ EwParams p) {
+    extern __shared__ float sacc[];                            // [C][2]
+    const int quads = p.C / 4, rows = 256 / quads;
+    const int q = threadIdx.x % quads, r0 = threadIdx.x / quads;
+    const int n = blockIdx.y;
+    const int64_t hw = (int64_t)p.H * p.W;
+    const int64_t pix0 = (int64_t)blockIdx.x * EW_PIX;
+    for (int i = threadIdx.x; i < 2 * p.C; i += 256) sacc[i] = 0.f;
+    __syncthreads();
+    float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+    for (int pr = r0; pr < EW_PIX; pr += rows) {
+        const int64_t pix = pix0 + pr;
+        if (pix >= hw) break;
+        const size_t o = ((size_t)n * hw + pix) * p.C + q * 4;
+        float4 v;
+        if (p.mode == 0) {
+            v = *reinterpret_cast<const float4 *>(p.a + o);
+            const float4 b = *reinterpret_cast<const float4 *>(p.b + o);
+            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+            if (p.c) {
+                const float4 c = *reinterpret_cast<const float4 *>(p.c + o);
+                v.x += c.x; v.y += c.y; v.z += c.z; v.w += c.w;
+            }
+        } else if (p.mode == 1) {
+            const int oy = (int)(pix / p.W), ox = (int)(pix % p.W);
+            const int W2 = 2 * p.W;
+            const float *s = p.a + (((size_t)n * 2 * p.H + 2 * oy) * W2 + 2 * ox) * p.C + q * 4;
+            const float4 a00 = *reinterpret_cast<const float4 *>(s), a01 = *reinterpret_cast<const float4 *>(s + p.C);
+            const float4 a10 = *reinterpret_cast<const float4 *>(s + (size_t)W2 * p.C);
+            const float4 a11 = *reinterpret_cast<const float4 *>(s + (size_t)W2 * p.C + p.C);
+            // F.avg_pool2d: (a00 + a01 + a10 + a11) / 4 in this summation order
+            v.x = (a00.x + a01.x + a10.x + a11.x) * 0.25f; v.y = (a00.y + a01.y + a10.y + a11.y) * 0.25f;
+            v.z = (a00.z + a01.z + a10.z + a11.z) * 0.25f; v.w = (a00.w + a01.w + a10.w + a11.w) * 0.25f;
+        } else {
+            const int oy = (int)(pix / p.W), ox = (int)(pix % p.W);
+            const int H = p.H / 2, W = p.W / 2;
+            const float sy = p.H > 1 ? (float)(H - 1) / (float)(p.H - 1) : 0.f, sx = p.W > 1 ? (float)(W - 1) / (float)(p.W - 1) : 0.f;
+            const float fy = sy * oy, fx = sx * ox;
+            const int iy = (int)floorf(fy), ix = (int)floorf(fx);
+            float wy[4], wx[4];
+            cubic_w4(fy - iy, wy);
+            cubic_w4(fx - ix, wx);
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int aa = 0; aa < 4; ++aa) {
+                const int yy = min(max(iy - 1 + aa, 0), H - 1);
+                float4 row = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int bb = 0; bb < 4; ++bb) {
+                    const int xx = min(max(ix - 1 + bb, 0), W - 1);
+                    const float4 t = *reinterpret_cast<const float4 *>(p.a + (((size_t)n * H + yy) * W + xx) * p.C + q * 4);
+                    row.x = fmaf(t.x, wx[bb], row.x); row.y = fmaf(t.y, wx[bb], row.y);
+                    row.z = fmaf(t.z, wx[bb], row.z); row.w = fmaf(t.w, wx[bb], row.w);
+                }
+                acc.x = fmaf(row.x, wy[aa], acc.x); acc.y = fmaf(row.y, wy[aa], acc.y);
+                acc.z = fmaf(row.z, wy[aa], acc.z); acc.w = fmaf(row.w, wy[aa], acc.w);
+            }
+            const float4 b = *reinterpret_cast<const float4 *>(p.b + o);
+            v = make_float4(acc.x + b.x, acc.y + b.y, acc.z + b.z, acc.w + b.w);
+        }
+        *reinterpret_cast<float4 *>(p.y + o) = v;
+        s1.x += v.x; s1.y += v.y; s1.z += v.z; s1.w += v.w;
+        s2.x = fmaf(v.x, v.x, s2.x); s2.y = fmaf(v.y, v.y, s2.y); s2.z = fmaf(v.z, v.z, s2.z); s2.w = fmaf(v.w, v.w, s2.w);
+    }
+    if (!p.stats) return;
+    atomicAdd(&sacc[(q * 4 + 0) * 2], s1.x); atomicAdd(&sacc[(q * 4 + 0) * 2 + 1], s2.x);
+    atomicAdd(&sacc[(q * 4 + 1) * 2], s1.y); atomicAdd(&sacc[(q * 4 + 1) * 2 + 1], s2.y);
+    atomicAdd(&sacc[(q * 4 + 2) * 2], s1.z); atomicAdd(&sacc[(q * 4 + 2) * 2 + 1], s2.z);
+    atomicAdd(&sacc[(q * 4 + 3) * 2], s1.w); atomicAdd(&sacc[(q * 4 + 3) * 2 + 1], s2.w);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * p.C; i += 256) atomicAdd(p.stats + (size_t)n * p.C * 2 + i, (double)sacc[i]);
+}
+
+// ---------------------------------------------------------------------------------------- layout adaptors
+// x [N][C][HW] -> y [N][HW][C] (+ stats).  grid (ceil(HW / 32), N), 256 threads, C <= 256.
+__global__ void __launch_bounds__(256) k_nchw_to_nhwc(const float *__restrict__ x, float *__restrict__ y,
+                                                      double *__restrict__ stats, int C, int64_t HW) {
+    extern __shared__ float tile[];                            // [32][C + 1]
+    const int n = blockIdx.y;
+    const int64_t p0 = (int64_t)blockIdx.x * 32;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int c = w; c < C; c += 8) {
+        const int64_t pix = p0 + lane;
+        const float v = pix < HW ? x[((size_t)n * C + c) * HW + pix] : 0.f;
+        tile[lane * (C + 1) + c] = v;
+        if (stats) {
+            float s1 = v, s2 = v * v;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+            }
+            if (lane == 0) {
+                atomicAdd(stats + ((size_t)n * C + c) * 2, (double)s1);
+                atomicAdd(stats + ((size_t)n * C + c) * 2 + 1, (double)s2);
+            }
+        }
+    }
+    __syncthreads();
+    const int64_t npx = min((int64_t)32, HW - p0);
+    for (int i = threadIdx.x; i < npx * C; i += 256) {
+        const int px = i / C, c = i % C;
+        y[((size_t)n * HW + p0) * C + i] = tile[px * (C + 1) + c];
+    }
+}
+
+// x [N][HW][Cs] channels [c_off, c_off + C) -> y [N][C][HW]
+__global__ void k_nhwc_to_nchw(const float *__restrict__ x, float *__restrict__ y, int N, int C, int Cs, int c_off, int64_t HW) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)N * C * HW) return;
+    const int64_t pix = i % HW;
+    const int c = (int)((i / HW) % C), n = (int)(i / (HW * C));
+    y[i] = x[((size_t)n * HW + pix) * Cs + c_off + c];
+}
+
+// ---------------------------------------------------------------------------------------- 7 x 7 output head (Cout <= 3)
+// x fp32 NHWC [N][H][W][64], w torch layout [Cout][64][7][7], reflection pad 3, y NCHW [N][Cout][H][W], tanh optional
+__global__ void __launch_bounds__(128) k_conv7_head(const float *__restrict__ x, const float *__restrict__ w,
+                                                    const float *__restrict__ bias, float *__restrict__ y, int N, int H,
+                                                    int W, int Cout, int act) {
+    __shared__ float4 sw[49 * 16 * 3];                         // [tap][c4][co] -> float4 over 4 consecutive input channels
+    for (int i = threadIdx.x; i < 49 * 16 * 3; i += blockDim.x) {
+        const int co = i % 3, c4 = (i / 3) & 15, tap = i / 48;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (co < Cout) {
+            const float *s = w + ((size_t)co * 64 + c4 * 4) * 49 + tap;
+            v = make_float4(s[0], s[49], s[98], s[147]);
+        }
+        sw[i] = v;
+    }
+    __syncthreads();
+    // 16 x 8 pixel tile per block so that the 7 x 7 windows of neighbouring threads overlap in L1
+    const int tx = blockIdx.x % ((W + 15) / 16), ty = blockIdx.x / ((W + 15) / 16);
+    const int n = blockIdx.y;
+    const int ox = tx * 16 + (threadIdx.x & 15), oy = ty * 8 + (threadIdx.x >> 4);
+    if (ox >= W || oy >= H) return;
+    float acc[3] = {0.f, 0.f, 0.f};
+    for (int kh = 0; kh < 7; ++kh) {
+        int iy = oy - 3 + kh;
+        iy = iy < 0 ? -iy : (iy >= H ? 2 * H - 2 - iy : iy);
+        for (int kw = 0; kw < 7; ++kw) {
+            int ix = ox - 3 + kw;
+            ix = ix < 0 ? -ix : (ix >= W ? 2 * W - 2 - ix : ix);
+            const float4 *src = reinterpret_cast<const float4 *>(x + (((size_t)n * H + iy) * W + ix) * 64);
+            const float4 *wt = sw + (kh * 7 + kw) * 48;
+#pragma unroll
+            for (int c4 = 0; c4 < 16; ++c4) {
+                const float4 v = __ldg(src + c4);
+#pragma unroll
+                for (int co = 0; co < 3; ++co) {
+                    const float4 ww = wt[c4 * 3 + co];
+                    acc[co] = fmaf(v.x, ww.x, acc[co]); acc[co] = fmaf(v.y, ww.y, acc[co]);
+                    acc[co] = fmaf(v.z, ww.z, acc[co]); acc[co] = fmaf(v.w, ww.w, acc[co]);
+                }
+            }
+        }
+    }
+    for (int co = 0; co < Cout; ++co) {
+        float v = acc[co] + (bias ? bias[co] : 0.f);
+        if (act == 2) v = tanhf(v);
+        else if (act == 1) v = fmaxf(v, 0.f);
+        y[(((size_t)n * Cout + co) * H + oy) * W + ox] = v;
+    }
+}
+
+}  // namespace icon
+
+using namespace icon;
+
+extern "C" int icon_norm_finalize(const double *stats, const float *gamma, const float *beta, float *scale_shift, int N, int C,
+                                  int groups, double count, float eps, icon_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    ICON_CHECK_ARG(stats && scale_shift && N > 0 && C > 0 && count > 0, "icon_norm_finalize: bad argument");
+    ICON_CHECK_ARG(groups <= 0 || C % groups == 0, "icon_norm_finalize: C %% groups != 0");
+    ICON_CHECK_ARG((gamma == nullptr) == (beta == nullptr), "icon_norm_finalize: gamma and beta go together");
+    k_norm_finalize<<<(N * C + 127) / 128, 128, 0, stream>>>(stats, gamma, beta, (float2 *)scale_shift, N, C, groups, count, eps);
+    ICON_LAUNCHED();
+    return ICON_OK;
+}
+
+extern "C" int icon_act_nhwc(const float *x, int Cs_in, int ci_off, const float *scale_shift, const float *res, void *hi,
+                             void *lo, float *f32, int N, int H, int W, int C, int Cp, int halo, int s2d, int relu,
+                             icon_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    ICON_CHECK_ARG(x && N > 0 && H > 0 && W > 0 && C > 0 && Cp >= C && Cp % 8 == 0, "icon_act_nhwc: bad argument");
+    ICON_CHECK_ARG((hi == nullptr) == (lo == nullptr) && (hi || f32), "icon_act_nhwc: hi and lo go together; need an output");
+    ICON_CHECK_ARG(!s2d || (halo == 0 && H % 2 == 0 && W % 2 == 0), "icon_act_nhwc: space-to-depth needs even H, W and no halo");
+    ICON_CHECK_ARG(halo >= 0 && halo < H && halo < W, "icon_act_nhwc: reflection halo %d needs halo < H, W", halo);
+    ICON_CHECK_ARG(ci_off >= 0 && ci_off + C <= Cs_in, "icon_act_nhwc: channel slice outside the input tensor");
+    ActParams p{};
+    p.x = x; p.ss = (const float2 *)scale_shift; p.res = res; p.hi = (__half *)hi; p.lo = (__half *)lo; p.f32 = f32;
+    p.N = N; p.H = H; p.W = W; p.C = C; p.Cs_in = Cs_in; p.ci_off = ci_off; p.Cp = Cp; p.P = halo; p.s2d = s2d; p.relu = relu;
+    const int64_t total = (int64_t)N * (s2d ? H : H + 2 * halo) * (s2d ? W : W + 2 * halo) * (Cp / 8);
+    k_act_nhwc<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(p);
+    ICON_LAUNCHED();
+    return ICON_OK;
+}
+
+extern "C" int icon_ew_nhwc(int mode, const float *a, const float *b, const float *c, float *y, double *stats, int N, int H,
+                            int W, int C, icon_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    ICON_CHECK_ARG(a && y && N > 0 && H > 0 && W > 0 && mode >= 0 && mode <= 2, "icon_ew_nhwc: bad argument");
+    ICON_CHECK_ARG(mode == 1 || b, "icon_ew_nhwc: second operand missing");
+    ICON_CHECK_ARG(C % 4 == 0 && C <= 1024 && 256 % (C / 4) == 0, "icon_ew_nhwc: C=%d must be a power of two in [4, 1024]", C);
+    ICON_CHECK_ARG(mode != 2 || (H % 2 == 0 && W % 2 == 0), "icon_ew_nhwc: upsample output must be even");
+    EwParams p{};
+    p.a = a; p.b = b; p.c = c; p.y = y; p.stats = stats; p.N = N; p.H = H; p.W = W; p.C = C; p.mode = mode;
+    dim3 grid((unsigned)(((int64_t)H * W + EW_PIX - 1) / EW_PIX), (unsigned)N);
+    k_ew_nhwc<<<grid, 256, 2 * C * sizeof(float), stream>>>(p);
+    ICON_LAUNCHED();
+    return ICON_OK;
+}
+
+extern "C" int icon_nchw_to_nhwc(const float *x, float *y, double *stats, int N, int C, int64_t HW, icon_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    ICON_CHECK_ARG(x && y && N > 0 && C > 0 && C <= 256 && HW > 0, "icon_nchw_to_nhwc: bad argument (C <= 256)");
+    dim3 grid((unsigned)((HW + 31) / 32), (unsigned)N);
+    k_nchw_to_nhwc<<<grid, 256, 32 * (C + 1) * sizeof(float), stream>>>(x, y, stats, C, HW);
+    ICON_LAUNCHED();
+    return ICON_OK;
+}
+
+extern "C" int icon_nhwc_to_nchw(const float *x, float *y, int N, int C, int Cs, int c_off, int64_t HW, icon_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    ICON_CHECK_ARG(x && y && N > 0 && C > 0 && c_off >= 0 && c_off + C <= Cs && HW > 0, "icon_nhwc_to_nchw: bad argument");
+    const int64_t total = (int64_t)N * C * HW;
+    k_nhwc_to_nchw<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(x, y, N, C, Cs, c_off, HW);
+    ICON_LAUNCHED();
+    return ICON_OK;
+}
+
+extern "C" int icon_conv7_head(const float *x, const float *w, const float *bias, float *y, int N, int H, int W, int Cin,
+                               int Cout, int act, icon_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    ICON_CHECK_ARG(x && w && y && N > 0 && H > 3 && W > 3, "icon_conv7_head: bad argument");
+    ICON_CHECK_ARG(Cin == 64 && Cout >= 1 && Cout <= 3, "icon_conv7_head: 64 -> (1..3) channels (FBNet.py:258)");
+    dim3 grid((unsigned)(((W + 15) / 16) * ((H + 7) / 8)), (unsigned)N);
+    k_conv7_head<<<grid, 128, 0, stream>>>(x, w, bias, y, N, H, W, Cout, act);
+    ICON_LAUNCHED();
+    return ICON_OK;
+}

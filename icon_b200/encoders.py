@@ -52,6 +52,25 @@ class ConvBlock(nn.Module):
             residual = C.conv2d(C.group_norm(x, self.bn4, relu=True), self.downsample[2])
         return C.cat_add((out1, out2, out3), residual)
 
+    def forward_nhwc(self, x):
+        """Same block on the NHWC path: x = nhwc.Raw with statistics; the three convs write their channel slices
+        of ONE output tensor (torch.cat for free), every GroupNorm reads the sums its producer accumulated."""
+        from . import nhwc as T
+        c1, c2, c3 = self.conv1.out_channels, self.conv2.out_channels, self.conv3.out_channels
+        y = torch.empty(x.N, x.H, x.W, c1 + c2 + c3, dtype=torch.float32, device=x.t.device)
+        op, _ = T.act(x, T.finalize(x, self.bn1), relu=True)
+        r1 = T.conv(op, self.conv1, out=y, co_off=0)
+        op, _ = T.act(r1, T.finalize(r1, self.bn2), relu=True)
+        r2 = T.conv(op, self.conv2, out=y, co_off=c1)
+        op, _ = T.act(r2, T.finalize(r2, self.bn3), relu=True)
+        T.conv(op, self.conv3, out=y, co_off=c1 + c2, stats=False)
+        if self.downsample is not None:
+            op, _ = T.act(x, T.finalize(x, self.bn4), relu=True)
+            residual = T.conv(op, self.downsample[2], stats=False).t
+        else:
+            residual = x.dense()
+        return T.add(y, residual)
+
 
 class HourGlass(nn.Module):
     """HGFilters.py:23-79."""
@@ -87,6 +106,17 @@ class HourGlass(nn.Module):
     def forward(self, x):
         return self._forward(self.depth, x)
 
+    def forward_nhwc(self, level, inp):
+        from . import nhwc as T
+        up1 = self._modules["b1_" + str(level)].forward_nhwc(inp)
+        low1 = self._modules["b2_" + str(level)].forward_nhwc(T.avg_pool2(inp.dense()))
+        if level > 1:
+            low2 = self.forward_nhwc(level - 1, low1)
+        else:
+            low2 = self._modules["b2_plus_" + str(level)].forward_nhwc(low1)
+        low3 = self._modules["b3_" + str(level)].forward_nhwc(low2)
+        return T.bicubic_up2_add(low3.dense(), up1.dense())
+
 
 class HGFilter(nn.Module):
     """HGFilters.py:82-197 (hg_down='ave_pool', norm='group')."""
@@ -120,6 +150,8 @@ class HGFilter(nn.Module):
 
     def _forward_eager(self, x):
         C = _conv_ops()
+        if C._IMPL == "auto" and x.shape[2] % 16 == 0 and x.shape[3] % 16 == 0:
+            return self._forward_nhwc(x)
         with torch.no_grad():
             x = C.group_norm(C.conv2d(x, self.conv1), self.bn1, relu=True)
             x = C.avg_pool2(self.conv2(x))
@@ -138,6 +170,35 @@ class HGFilter(nn.Module):
                     ll = C.conv2d(ll, self._modules["bl" + str(i)])
                     tmp_out_ = C.conv2d(tmp_out, self._modules["al" + str(i)])
                     previous = C.add3(previous, ll, tmp_out_)
+        return outputs
+
+    def _forward_nhwc(self, x):
+        """HGFilters.py:161-197 on the NHWC / TMA / tcgen05 path (icon_b200/nhwc.py).  The 7x7 stride-2 stem (Cin = 3..9)
+        runs on the FP32 kernel in NCHW; everything after it is NHWC."""
+        C = _conv_ops()
+        from . import nhwc as T
+        with torch.no_grad():
+            x = C.group_norm(C.conv2d(x, self.conv1), self.bn1, relu=True)      # NCHW, [N, 64, H/2, W/2]
+            x = T.raw_from_nchw(x)                                               # + statistics for conv2.bn1
+            x = T.avg_pool2(self.conv2.forward_nhwc(x).dense())
+            x = self.conv3.forward_nhwc(x)
+            x = self.conv4.forward_nhwc(x)
+            previous = x
+            outputs = []
+            for i in range(self.num_modules):
+                m = self._modules["m" + str(i)]
+                hg = m.forward_nhwc(m.depth, previous)
+                ll = self._modules["top_m_" + str(i)].forward_nhwc(hg)
+                op, _ = T.act(ll)                                                # conv_last reads ll itself (no norm)
+                r = T.conv(op, self._modules["conv_last" + str(i)])
+                op_ll, _ = T.act(r, T.finalize(r, self._modules["bn_end" + str(i)]), relu=True)
+                tmp_out = T.conv(op_ll, self._modules["l" + str(i)], stats=False)
+                outputs.append(T.to_nchw(tmp_out))
+                if i < self.num_modules - 1:
+                    llb = T.conv(op_ll, self._modules["bl" + str(i)], stats=False)
+                    op_t, _ = T.act(tmp_out)
+                    t2 = T.conv(op_t, self._modules["al" + str(i)], stats=False)
+                    previous = T.add(previous.dense(), llb.t, t2.t)
         return outputs
 
 
@@ -194,6 +255,10 @@ class GlobalGenerator(nn.Module):
     def _forward_eager(self, x):
         C = _conv_ops()
         m = self.model
+        if (C._IMPL == "auto" and x.shape[2] % (1 << self.n_downsampling) == 0 and x.shape[3] % (1 << self.n_downsampling) == 0
+                and m[1].out_channels == 64 and m[-2 if isinstance(m[-1], nn.Tanh) else -1].out_channels <= 3
+                and (x.shape[2] >> self.n_downsampling) >= 2 and (x.shape[3] >> self.n_downsampling) >= 2):
+            return self._forward_nhwc(x)
         with torch.no_grad():
             y = C.instance_norm(C.conv2d(x, m[1], reflect=3), relu=True)
             idx = 4
@@ -208,6 +273,41 @@ class GlobalGenerator(nn.Module):
                 idx += 3
             y = C.conv2d(y, m[idx + 1], reflect=3, tanh=(len(m) > idx + 2))
         return y
+
+    def _forward_nhwc(self, x):
+        """FBNet.py:216-264 on the NHWC / TMA / tcgen05 path: every InstanceNorm reads the sums its producing conv
+        accumulated; ReflectionPad2d = halo written by the normalising pass; stride-2 convs read space-to-depth
+        planes; ConvTranspose2d = 4 output phases.  Stem (Cin = 6) on the FP32 kernel in NCHW, head on k_conv7_head."""
+        C = _conv_ops()
+        from . import nhwc as T
+        m = self.model
+        nd, nb = self.n_downsampling, self.n_blocks
+        with torch.no_grad():
+            raw = T.raw_from_nchw(C.conv2d(x, m[1], reflect=3))
+            idx = 4
+            for _ in range(nd):
+                op, _ = T.act(raw, T.finalize(raw), relu=True, s2d=True)
+                raw = T.conv(op, m[idx])
+                idx += 3
+            if nb > 0:
+                op, cur = T.act(raw, T.finalize(raw), relu=True, halo=1, f32=True)
+                for b in range(nb):
+                    blk = m[idx].conv_block
+                    r1 = T.conv(op, blk[1])
+                    op1, _ = T.act(r1, T.finalize(r1), relu=True, halo=1)
+                    r2 = T.conv(op1, blk[5])
+                    last = b == nb - 1
+                    op, cur = T.act(r2, T.finalize(r2), res=cur, halo=0 if last else 1, f32=not last)
+                    idx += 1
+            else:
+                op, _ = T.act(raw, T.finalize(raw), relu=True)
+            f32 = None
+            for u in range(nd):
+                raw = T.conv_transpose(op, m[idx])
+                last = u == nd - 1
+                op, f32 = T.act(raw, T.finalize(raw), relu=True, operand=not last, f32=last)
+                idx += 3
+            return T.conv7_head(f32, m[idx + 1], tanh=(len(m) > idx + 2))
 
 
 class NormalNet(nn.Module):

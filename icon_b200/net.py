@@ -60,6 +60,8 @@ def init_net(net, init_gain=0.02):
             nn.init.normal_(m.weight.data, 1.0, init_gain)
             nn.init.constant_(m.bias.data, 0.0)
     net.apply(init_func)
+    from .nhwc import invalidate_packed      # `.data` writes do not bump tensor versions: drop packed blobs / graphs
+    invalidate_packed(net)
     return net
 
 

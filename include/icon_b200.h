@@ -215,6 +215,39 @@ size_t icon_conv2d_tc_workspace_bytes(int N, int Cout, int OH, int OW, int split
 int icon_conv2d_tc(const float *x, const void *wt_packed, const float *bias, const float *res, float *y, int N,
                    int Cin, int H, int W, int Cout, int KH, int KW, int stride, int pad, int out_pad, int reflect,
                    int transposed, int act, int n_tile, int splits, void *ws, size_t ws_bytes, icon_stream_t stream);
+/* ---- NHWC encoder path (csrc/conv_nhwc.cu, csrc/act_nhwc.cu): activations between layers are NHWC, pre-split
+ * x = hi + lo into two fp16 tensors [N * nplanes][Hp][Wp][Cp] (Cp % 64 == 0) by icon_act_nhwc.
+ *
+ * icon_conv_nhwc: implicit-GEMM convolution on tcgen05, A operand staged by 4-D tiled TMA loads straight from the
+ *   hi / lo tensors (`dims` = tensor-map extents innermost first, `strides` = element strides of dims 1..3), weights
+ *   from `wt_packed` (per n_tile output channels and per chunk a K-major SWIZZLE_128B fp16 hi tile followed by the lo
+ *   tile; `wt_chunks` chunks per tile, chunk index = wtap * cpt + channel block).  The launch covers a logical
+ *   Ht x Wt grid per image; output pixel (a, b) is written to out[n][a * osy + ooy][b * osx + oox][co_off + co] of an
+ *   fp32 NHWC tensor with Cs channels (channel slices = concatenation for free; osy = 2 = one phase of a transposed
+ *   convolution).  `taps`: ntaps x (dy, dx, plane, wtap) -- the A box of tap t is read at (y0 + dy, x0 + dx) of image
+ *   n * nplanes + plane (out-of-range coordinates read zeros = zero padding).  stats (optional, zeroed by the
+ *   caller): [N][Cout][2] doubles receive per-channel sum / sum of squares of the result (bias included).
+ * icon_norm_finalize: stats -> [N][C] (scale, shift) for InstanceNorm2d (groups = 0) / GroupNorm(groups) with affine.
+ * icon_act_nhwc: y = [relu](x * scale + shift) [+ res]  -> hi / lo operand tensors (halo > 0: reflection halo;
+ *   s2d = 1: four parity planes for a stride-2 consumer; channels padded to Cp with zeros) and / or fp32 NHWC.
+ * icon_ew_nhwc: mode 0 a + b (+ c), 1 avg_pool2(a), 2 b + bicubic_up2(a, align_corners); optional stats of the result.
+ * icon_nchw_to_nhwc / icon_nhwc_to_nchw: layout adaptors (the former with optional stats).
+ * icon_conv7_head: 7 x 7 reflection-padded 64 -> (1..3) channel convolution from fp32 NHWC to NCHW, act 2 = tanh. */
+size_t icon_conv_nhwc_workspace_bytes(int N, int Ht, int Wt, int Cout, int splits);
+int icon_conv_nhwc(const void *a_hi, const void *a_lo, const int64_t *dims, const int64_t *strides, const void *wt_packed,
+                   int wt_chunks, const float *bias, float *out, int OHf, int OWf, int Cs, int co_off, int Cout, int N,
+                   int Ht, int Wt, int osy, int osx, int ooy, int oox, int nplanes, int ntaps, const int *taps, int cpt,
+                   int n_tile, int splits, double *stats, void *ws, size_t ws_bytes, icon_stream_t stream);
+int icon_norm_finalize(const double *stats, const float *gamma, const float *beta, float *scale_shift, int N, int C,
+                       int groups, double count, float eps, icon_stream_t stream);
+int icon_act_nhwc(const float *x, int Cs_in, int ci_off, const float *scale_shift, const float *res, void *hi, void *lo,
+                  float *f32, int N, int H, int W, int C, int Cp, int halo, int s2d, int relu, icon_stream_t stream);
+int icon_ew_nhwc(int mode, const float *a, const float *b, const float *c, float *y, double *stats, int N, int H, int W,
+                 int C, icon_stream_t stream);
+int icon_nchw_to_nhwc(const float *x, float *y, double *stats, int N, int C, int64_t HW, icon_stream_t stream);
+int icon_nhwc_to_nchw(const float *x, float *y, int N, int C, int Cs, int c_off, int64_t HW, icon_stream_t stream);
+int icon_conv7_head(const float *x, const float *w, const float *bias, float *y, int N, int H, int W, int Cin, int Cout,
+                    int act, icon_stream_t stream);
 int icon_group_norm(const float *x, const float *gamma, const float *beta, const float *res, float *y, int N,
                     int C, int HW, int groups, float eps, int relu, void *stats_ws /* 16*N*groups bytes or NULL */,
                     icon_stream_t stream);

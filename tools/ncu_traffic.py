@@ -20,7 +20,7 @@ WANT = {
     "dram__bytes_read.sum": "dram_read", "dram__bytes_write.sum": "dram_write",
     "gpu__time_duration.sum": "duration", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active": "tensor_pct",
     "sm__inst_executed_pipe_tensor.sum": "tensor_inst", "sm__warps_active.avg.pct_of_peak_sustained_active": "warps_pct",
-    "sm__issue_active.avg.pct_of_peak_sustained_active": "issue_pct", "launch__registers_per_thread": "regs",
+    "sm__issue_active.avg.pct_of_peak_sustained_elapsed": "issue_pct", "launch__registers_per_thread": "regs",
     "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed": "dram_pct",
 }
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12, "nsecond": 1e-6, "usecond": 1e-3, "msecond": 1.0,
