@@ -140,3 +140,17 @@ extern "C" int icon_profile_last_query(float *h_ms) {
 extern "C" int icon_version(void) { return 1; }
 extern "C" const char *icon_last_error(void) { return icon::g_err; }
 extern "C" int64_t icon_launch_count(void) { return icon::g_launches.load(); }
+
+namespace icon {
+int device_sm_count() {
+    static int counts[ICON_MAX_DEVICES] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= ICON_MAX_DEVICES) return 148;
+    if (!counts[dev]) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        counts[dev] = n;
+    }
+    return counts[dev];
+}
+}  // namespace icon

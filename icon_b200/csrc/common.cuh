@@ -38,6 +38,19 @@ void count_launch(int n = 1);
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// cudaFuncSetAttribute is per DEVICE, the process may use several (the reference's cfg.test_gpus): remember which
+// devices a kernel's opt-in has been done on.  `flags` = one static array per call site.
+constexpr int ICON_MAX_DEVICES = 64;
+static inline bool device_needs_setup(bool (&flags)[ICON_MAX_DEVICES], int *dev_out = nullptr) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= ICON_MAX_DEVICES) { if (dev_out) *dev_out = 0; return true; }
+    if (dev_out) *dev_out = dev;
+    if (flags[dev]) return false;
+    flags[dev] = true;
+    return true;
+}
+int device_sm_count();    // multiprocessors of the CURRENT device (cached per device)
+
 // carve a workspace
 struct Carver {
     char *base;

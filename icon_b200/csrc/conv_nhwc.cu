@@ -306,13 +306,9 @@ template <int NT, int STAGES>
 static int launch_conv_nhwc(const CUtensorMap &mh, const CUtensorMap &ml, const ConvNhwcParams &p, dim3 grid,
                             cudaStream_t stream) {
     constexpr int smem = STAGES * (2 * 128 * 128 + NT * 256) + 1024;
-    int dev = 0;
-    ICON_CUDA(cudaGetDevice(&dev));
-    static bool attr_set[64] = {};
-    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    static bool attr_set[ICON_MAX_DEVICES] = {};
+    if (device_needs_setup(attr_set))
         ICON_CUDA(cudaFuncSetAttribute(k_conv_nhwc<NT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        if (dev >= 0 && dev < 64) attr_set[dev] = true;
-    }
     k_conv_nhwc<NT, STAGES><<<grid, CN_THREADS, smem, stream>>>(mh, ml, p);
     ICON_LAUNCHED();
     return ICON_OK;

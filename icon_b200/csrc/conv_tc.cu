@@ -274,12 +274,10 @@ __global__ void k_splitk_finish(const float *__restrict__ part, int splits, cons
 
 template <int NT>
 static int launch_conv_tc(const ConvTcParams &p, dim3 grid, cudaStream_t stream) {
-    static bool attr_set = false;
+    static bool attr_set[ICON_MAX_DEVICES] = {};
     const int smem = 2 * NT * 256 + 1024;
-    if (!attr_set) {
+    if (device_needs_setup(attr_set))
         ICON_CUDA(cudaFuncSetAttribute(k_conv_tc<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
-    }
     k_conv_tc<NT><<<grid, CT_THREADS, smem, stream>>>(p);
     ICON_LAUNCHED();
     return ICON_OK;

@@ -293,11 +293,9 @@ constexpr size_t MLP_SMEM = (16 * MP + 10240 + 256 * MP) * sizeof(float);
 
 template <int MODE>
 static int launch_mlp(const QueryParams &q, cudaStream_t stream) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[ICON_MAX_DEVICES] = {};
+    if (device_needs_setup(attr_set))
         ICON_CUDA(cudaFuncSetAttribute(k_query_mlp<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_SMEM));
-        attr_set = true;
-    }
     unsigned nblk = (unsigned)((q.N + MP - 1) / MP);
     k_query_mlp<MODE><<<nblk, MT, MLP_SMEM, stream>>>(q);
     ICON_LAUNCHED();

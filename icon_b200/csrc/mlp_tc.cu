@@ -464,22 +464,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_query_mlp_tc(QueryParams q, c
     }
 }
 
-static int g_sm_count = 0;
-
 template <int MODE>
 int launch_mlp_tc_t(const QueryParams &q, const void *blob, cudaStream_t stream) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[ICON_MAX_DEVICES] = {};
+    if (device_needs_setup(attr_set))
         ICON_CUDA(cudaFuncSetAttribute(k_query_mlp_tc<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-        attr_set = true;
-    }
-    if (!g_sm_count) {
-        int dev = 0;
-        ICON_CUDA(cudaGetDevice(&dev));
-        ICON_CUDA(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
-    }
+    const int sms = device_sm_count();
     const int64_t ntiles = (q.N + TC_M - 1) / TC_M;
-    const unsigned grid = (unsigned)(ntiles < g_sm_count ? ntiles : g_sm_count);
+    const unsigned grid = (unsigned)(ntiles < sms ? ntiles : sms);
     k_query_mlp_tc<MODE><<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(q, (const uint8_t *)blob);
     ICON_LAUNCHED();
     return ICON_OK;

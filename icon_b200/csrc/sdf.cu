@@ -471,13 +471,12 @@ int run_sdf(const float *points, int64_t sc, int64_t sn, int64_t N, const float 
     ICON_CUDA(cudaMemsetAsync(w.count, 0, sizeof(int32_t) * (NBIN + 1), stream));       // reuse as cursor
     k_points_scatter<<<nblk, 256, 0, stream>>>(w.bid, N, w.offset, w.count, w.perm);
     ICON_LAUNCHED();
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[ICON_MAX_DEVICES] = {};
+    if (device_needs_setup(attr_set)) {
 #define ICON_SDF_ATTR(P) ICON_CUDA(cudaFuncSetAttribute(k_sdf_warp<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                                         (int)(sizeof(WarpSmem<fr_cap(P)>) * (SW_T / 32))))
         ICON_SDF_ATTR(32); ICON_SDF_ATTR(16); ICON_SDF_ATTR(8); ICON_SDF_ATTR(4); ICON_SDF_ATTR(2); ICON_SDF_ATTR(1);
 #undef ICON_SDF_ATTR
-        attr_set = true;
     }
     profile_mark(1, stream);
     // the kernel needs many warps in flight to hide the latency of its tree walk, so the fewer points a call has the

@@ -93,8 +93,11 @@ class Seg3dLossless(nn.Module):
         return occ
 
     def export_mesh(self, occupancys):
-        """seg3d_lossless.py:583-604: marching cubes at balance_value; returns CPU tensors."""
-        verts, faces = ops.marching_cubes(occupancys, self.balance_value)
+        """seg3d_lossless.py:583-604; returns CPU tensors.  The reference passes `self.balance_value` only to PyMCubes
+        (grid > 256^3, :592); the kaolin branch (:599) runs voxelgrids_to_trianglemeshes at its default iso 0.5."""
+        R = occupancys.shape[0]
+        iso = self.balance_value if (R - 1) > 256 else 0.5
+        verts, faces = ops.marching_cubes(occupancys, iso)
         return verts.cpu(), faces.cpu()
 
     # ---- training-time preview (apps/ICON.py:694-727 render_func); off the inference hot path, plain torch ops

@@ -271,19 +271,29 @@ def grid_dilate(mask, k):
 
 
 def grid_compact(mask_xyz, done, R_last, b_min, b_max):
-    """-> (points [1,n,3] f32, indices [n] i64); one host sync to learn n."""
+    """-> (points [1,n,3] f32, indices [n] i64); one host sync to learn n.
+
+    The boundary set is a few percent of the grid, so the output buffers are sized for 1/16 of it (at least 256 k
+    points) instead of R^3; the kernel never writes past the capacity it is given, and the rare overflow re-runs
+    once with the exact count (`done` is restored first: the write pass marks what it emitted)."""
     R = mask_xyz.shape[0]
     dev = mask_xyz.device
     n_all = R * R * R
     nbytes = lib.icon_compact_workspace_bytes(R)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    pts = torch.empty(n_all, 3, dtype=torch.float32, device=dev)
-    idx = torch.empty(n_all, dtype=torch.int64, device=dev)
     cnt = torch.zeros(1, dtype=torch.int64, device=dev)
-    check(lib.icon_grid_compact(_p(mask_xyz), _p(done), R, R_last, _hf(b_min), _hf(b_max), _p(pts), _p(idx),
-                                n_all, _p(cnt), _p(ws), nbytes, _stream()), "icon_grid_compact")
-    n = int(cnt.item())
-    return pts[:n].unsqueeze(0), idx[:n]
+    cap = min(n_all, max(1 << 18, n_all // 16))
+    backup = done.clone() if cap < n_all else None
+    while True:
+        pts = torch.empty(cap, 3, dtype=torch.float32, device=dev)
+        idx = torch.empty(cap, dtype=torch.int64, device=dev)
+        check(lib.icon_grid_compact(_p(mask_xyz), _p(done), R, R_last, _hf(b_min), _hf(b_max), _p(pts), _p(idx),
+                                    cap, _p(cnt), _p(ws), nbytes, _stream()), "icon_grid_compact")
+        n = int(cnt.item())
+        if n <= cap:
+            return pts[:n].unsqueeze(0), idx[:n]
+        done.copy_(backup)
+        cap, backup = n, None
 
 
 def grid_scatter(occ, indices, values):
@@ -310,7 +320,8 @@ def grid_count_above(occ, balance):
 
 # --------------------------------------------------------------------------- marching cubes
 def marching_cubes(occ, iso=0.5):
-    """export_mesh on the device: occ [R,R,R] -> (verts [Nv,3] f32|f64 xyz, faces [Nf,3] i64), CUDA."""
+    """export_mesh on the device: occ [R,R,R] -> (verts [Nv,3] f32|f64 xyz, faces [Nf,3] i64), CUDA.
+    (engine.Seg3dLossless.export_mesh chooses `iso` per branch the way the reference does.)"""
     _need_cuda(occ)
     o = occ.detach().float().contiguous()
     R = o.shape[0]
