@@ -319,9 +319,14 @@ def grid_count_above(occ, balance):
 
 
 # --------------------------------------------------------------------------- marching cubes
-def marching_cubes(occ, iso=0.5):
+def marching_cubes(occ, iso=0.5, order="edge"):
     """export_mesh on the device: occ [R,R,R] -> (verts [Nv,3] f32|f64 xyz, faces [Nf,3] i64), CUDA.
-    (engine.Seg3dLossless.export_mesh chooses `iso` per branch the way the reference does.)"""
+    (engine.Seg3dLossless.export_mesh chooses `iso` per branch the way the reference does.)
+
+    order="edge" (default): vertex ids ascend with the owning grid edge.  order="lex":
+    the same mesh re-indexed the way a triangle-soup + `torch.unique(dim=0)` merge numbers it (rows sorted
+    lexicographically, coincident vertices collapsed) -- the order SURVEY 8c attributes to kaolin; an optional
+    compatibility re-index done with torch's sort-based unique, off the timed path."""
     _need_cuda(occ)
     o = occ.detach().float().contiguous()
     R = o.shape[0]
@@ -337,6 +342,12 @@ def marching_cubes(occ, iso=0.5):
     faces = torch.empty(nt, 3, dtype=torch.int64, device=o.device)
     check(lib.icon_mc_emit(_p(o), R, float(iso), padded, _p(ws), _p(verts), _p(faces), nv, nt, _stream()),
           "icon_mc_emit")
+    if order == "lex" and nv > 0:
+        # emitted columns are (k, j, i) = xyz; the soup is merged in the (i, j, k) frame, so sort on reversed columns
+        u, inv = torch.unique(verts.flip(1), dim=0, return_inverse=True)
+        verts, faces = u.flip(1).contiguous(), inv[faces]
+    elif order not in ("edge", "lex"):
+        raise _C.IconError("marching_cubes: order must be 'edge' or 'lex'")
     return verts, faces
 
 

@@ -25,10 +25,22 @@ contract that the CUDA kernels reproduce bit for bit:
   contract "plain" (PyMCubes branch): same, without padding, fp64 coordinates.
 
 `export_mesh` then applies the reference's own `[:, [2,1,0]]` / `[:, [0,2,1]]` permutations.
+
+Second selectable vertex order, `order="lex"` -- what SURVEY 8c believes kaolin's merge does: the triangle soup's
+vertices are merged with `torch.unique(dim=0)`, i.e. vertices sorted lexicographically by coordinate row and
+coincident ones (an edge vertex landing exactly on a grid node is shared by up to 3 edges) collapsed; triangles keep
+soup order.  A user with the kaolin wheel can compare against either order; both are UNPINNED here.
+
+Public algorithm references (sources absent from /root/reference, wheels not installable offline):
+  kaolin 0.11.0   kaolin/ops/conversions/voxelgrid.py::voxelgrids_to_trianglemeshes -> unbatched_mcube CUDA op
+                  (kaolin/csrc/ops/conversions/unbatched_mcube/unbatched_mcube_cuda.cu: classifyVoxel / compactVoxels /
+                  generateTriangles2, after the NVIDIA CUDA-samples marchingCubes), iso default 0.5
+  PyMCubes        mcubes/src/marchingcubes.h::marching_cubes (P. Bourke's table, shared vertices created on first
+                  use along x-fastest scan), called as mcubes.marching_cubes(arr, isovalue)
 """
 import numpy as np
 
-from icon_b200.mc_tables import CORNERS, EDGE_CORNERS, TRI_TABLE, NUM_VERTS
+from .mc_table import CORNERS, EDGE_CORNERS, TRI_TABLE, NUM_VERTS      # the checker's own copy of the table
 
 
 def _edge_owner():
@@ -84,11 +96,23 @@ def marching_cubes(vol, iso=0.5, pad=True, dtype=np.float32):
     return verts, faces
 
 
-def export_mesh(occupancys, balance_value=0.5):
-    """seg3d_lossless.py:583-604 restated.  occupancys: [R,R,R] float array indexed [z,y,x]."""
+def lexicographic_merge(verts, faces):
+    """Edge-owned (verts, faces) -> the soup + `unique(dim=0)` order: rows sorted lexicographically, coincident rows
+    merged, faces remapped (triangle order unchanged)."""
+    if len(verts) == 0:
+        return verts, faces
+    u, inv = np.unique(verts, axis=0, return_inverse=True)
+    return u, inv.reshape(-1)[faces]
+
+
+def export_mesh(occupancys, balance_value=0.5, order="edge"):
+    """seg3d_lossless.py:583-604 restated.  occupancys: [R,R,R] float array indexed [z,y,x].
+    The kaolin branch (grid <= 256^3, :599) runs at kaolin's default iso 0.5; PyMCubes (:592) at balance_value."""
     final = np.ascontiguousarray(np.asarray(occupancys)[1:, 1:, 1:])
     if final.shape[0] > 256:
         v, t = marching_cubes(final, balance_value, pad=False, dtype=np.float64)
     else:
-        v, t = marching_cubes(final, balance_value, pad=True, dtype=np.float32)
+        v, t = marching_cubes(final, 0.5, pad=True, dtype=np.float32)
+    if order == "lex":
+        v, t = lexicographic_merge(v, t)
     return v[:, [2, 1, 0]], t[:, [0, 2, 1]]

@@ -111,6 +111,27 @@ def test_marching_cubes_plain_branch_above_256():
     assert np.array_equal(v.cpu().numpy(), rv)
 
 
+def test_marching_cubes_lexicographic_order_contract():
+    """order='lex' = triangle soup + unique(dim=0) numbering (the order SURVEY 8c attributes to kaolin): same surface,
+    vertices sorted by coordinate row with coincident ones merged; index-exact vs the oracle's restatement.  The
+    field has a node exactly at the iso value so that the merge really collapses vertices."""
+    dev = _cuda()
+    from icon_b200 import ops
+    from oracle import mcubes as OM
+    R = 41
+    a = torch.linspace(-1, 1, R)
+    z, y, x = torch.meshgrid(a, a, a, indexing="ij")
+    occ = (0.5 + (0.6 - torch.sqrt(x * x + y * y + z * z))).float()
+    occ[20, 20, 32] = 0.5                        # a grid node ON the level set: up to 3 edge vertices coincide there
+    v, f = ops.marching_cubes(occ.to(dev), 0.5, order="lex")
+    rv, rf = OM.export_mesh(occ.numpy(), 0.5, order="lex")
+    assert np.array_equal(f.cpu().numpy(), rf)
+    assert np.array_equal(v.cpu().numpy(), rv)
+    ve, fe = ops.marching_cubes(occ.to(dev), 0.5)
+    assert len(v) <= len(ve) and f.shape == fe.shape
+    assert torch.equal(v[f], ve[fe])             # identical triangles, vertex for vertex
+
+
 def test_end_to_end_engine_with_network_vs_oracle():
     """filter-less icon config: engine + fused query + marching cubes vs the CPU oracle chain."""
     dev = _cuda()

@@ -81,3 +81,16 @@ def test_shared_faces_match_between_neighbouring_cubes():
             a, b = seen[("hi", pat)], seen[("lo", pat)]
             assert len(a) == 1 and len(b) == 1, (axis, pat)
             assert a == b, (axis, pat)
+
+
+def test_oracle_table_is_an_independent_but_identical_copy():
+    """oracle/mc_table.py must not import the product's table, and the two must agree."""
+    import inspect
+    import oracle.mc_table as OT
+    import icon_b200.mc_tables as PT
+    assert "icon_b200" not in inspect.getsource(OT).split('"""', 2)[2]
+    assert OT.TRI_LIST == PT.TRI_LIST and OT.EDGE_CORNERS == PT.EDGE_CORNERS and OT.CORNERS == PT.CORNERS
+    for case in range(256):
+        inside = [(case >> c) & 1 for c in range(8)]
+        crossing = {e for e, (a, b) in enumerate(OT.EDGE_CORNERS) if inside[a] != inside[b]}
+        assert set(OT.TRI_LIST[case]) == crossing
