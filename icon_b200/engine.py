@@ -98,7 +98,9 @@ class Seg3dLossless(nn.Module):
         R = occupancys.shape[0]
         iso = self.balance_value if (R - 1) > 256 else 0.5
         verts, faces = ops.marching_cubes(occupancys, iso)
-        return verts.cpu(), faces.cpu()
+        v_cpu, f_cpu = verts.cpu(), faces.cpu()
+        v_cpu._icon_device_mesh = (verts, faces)      # lets icon_b200.mesh.clean_mesh skip the upload (apps/ICON.py:753-756)
+        return v_cpu, f_cpu
 
     # ---- training-time preview (apps/ICON.py:694-727 render_func); off the inference hot path, plain torch ops
     def find_vertices(self, sdf, direction="front"):

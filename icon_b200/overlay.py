@@ -45,7 +45,7 @@ def _replacements():
 
 
 def _patches():
-    from . import encoders, net, visibility, voxelize
+    from . import encoders, mesh, net, visibility, voxelize
 
     def make_define_G(reference_define_G):
         import torch.nn as nn
@@ -61,9 +61,9 @@ def _patches():
         return define_G
 
     return {
-        "lib.common.train_util": {"query_func": net.query_func,
+        "lib.common.train_util": {"query_func": net.query_func, "clean_mesh": mesh.clean_mesh,
                                   "get_visibility": visibility.get_visibility},      # duplicate at train_util.py:361
-        "lib.dataset.mesh_util": {"get_visibility": visibility.get_visibility,
+        "lib.dataset.mesh_util": {"get_visibility": visibility.get_visibility, "clean_mesh": mesh.clean_mesh,
                                   "read_smpl_constants": voxelize.read_smpl_constants},
         "lib.net.NormalNet": {"NormalNet": encoders.NormalNet},
         "lib.net.MLP": {"MLP": net.MLP},

@@ -248,6 +248,15 @@ int icon_nchw_to_nhwc(const float *x, float *y, double *stats, int N, int C, int
 int icon_nhwc_to_nchw(const float *x, float *y, int N, int C, int Cs, int c_off, int64_t HW, icon_stream_t stream);
 int icon_conv7_head(const float *x, const float *w, const float *bias, float *y, int N, int H, int W, int Cin, int Cout,
                     int act, icon_stream_t stream);
+/* ---- clean_mesh (csrc/clean.cu; reference lib/dataset/mesh_util.py:778-791: trimesh split + largest component).
+ * faces int64 [nf][3] indexing nv vertices.  _count: union-find over the vertices, picks the component with the most
+ * vertices (ties: the one containing the smallest vertex id), leaves the kept counts in d_counts[0..1] and the
+ * re-index tables in `ws`; _emit writes the compacted float32 vertices / int32 faces (ascending original order). */
+size_t icon_clean_mesh_workspace_bytes(int64_t nv, int64_t nf);
+int icon_clean_mesh_count(const int64_t *faces, int64_t nv, int64_t nf, void *ws, size_t ws_bytes, int64_t *d_counts,
+                          icon_stream_t stream);
+int icon_clean_mesh_emit(const void *verts, int verts_f64, const int64_t *faces, int64_t nv, int64_t nf, const void *ws,
+                         float *out_verts, int32_t *out_faces, icon_stream_t stream);
 int icon_group_norm(const float *x, const float *gamma, const float *beta, const float *res, float *y, int N,
                     int C, int HW, int groups, float eps, int relu, void *stats_ws /* 16*N*groups bytes or NULL */,
                     icon_stream_t stream);

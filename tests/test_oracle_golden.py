@@ -221,3 +221,18 @@ def test_stock_torch_encoder_restatement_matches_reference_goldens(golden_dir):
         y6 = OE.global_generator(gg, torch.from_numpy(g["gg_x"]))
     assert np.abs(y.numpy() - g["hg_y"]).max() <= 1e-5
     assert np.abs(y6.numpy() - g["gg_y"]).max() <= 1e-5
+
+
+def test_oracle_clean_mesh_on_two_tetrahedra():
+    """Known answer: two disjoint closed tetrahedra (4 and 4 vertices -> first maximum = the first), plus a fin
+    attached along a 3-face (non-manifold) edge, which trimesh's face adjacency ignores."""
+    import numpy as np
+    from oracle import mesh as OMesh
+    tet = np.array([[0, 1, 2], [0, 3, 1], [1, 3, 2], [0, 2, 3]])
+    verts = np.random.RandomState(0).rand(9, 3)
+    faces = np.concatenate([tet + 4, tet, [[0, 1, 8]]])          # tetra B first in face order, then A, then the fin
+    v, f = OMesh.clean_mesh(verts, faces)
+    assert OMesh.face_components(faces)[0] == 3                  # the fin is its own component: edge (0,1) has 3 faces
+    # both tetrahedra have 4 vertices; A keeps edge (0,1) out of its adjacency but stays connected through the rest
+    assert len(v) == 4 and len(f) == 4 and f.dtype == np.int32 and v.dtype == np.float32
+    assert np.array_equal(v, verts[4:8].astype(np.float32))      # first maximum in component (= face) order: B

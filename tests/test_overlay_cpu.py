@@ -78,8 +78,10 @@ assert LN.NormalNet is icon_b200.encoders.NormalNet and LN.VolumeEncoder is icon
 assert A.Seg3dLossless is icon_b200.engine.Seg3dLossless
 assert A.query_func is icon_b200.net.query_func and TU.query_func is icon_b200.net.query_func
 assert A.get_visibility is icon_b200.visibility.get_visibility
+import icon_b200.mesh
+assert A.clean_mesh is icon_b200.mesh.clean_mesh and MU.clean_mesh is icon_b200.mesh.clean_mesh
 # names of the patched modules that are NOT on the accelerated path are still the reference's own objects
-for name in ("SMPLX", "update_mesh_shape_prior_losses", "load_checkpoint", "cal_sdf_batch", "feat_select"):
+for name in ("SMPLX", "update_mesh_shape_prior_losses", "load_checkpoint", "cal_sdf_batch", "feat_select", "remesh"):
     assert getattr(MU, name).__module__ == "lib.dataset.mesh_util", name
 for name in ("batch_mean", "accumulate", "calc_error", "tf_log_convert", "bar_log_convert", "export_cfg"):
     assert getattr(TU, name).__module__ == "lib.common.train_util", name
