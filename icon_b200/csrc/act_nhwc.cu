@@ -118,6 +118,8 @@ struct EwParams {
     double *stats;           // [N][C][2] or null
     int N, H, W, C;          // OUTPUT dims
     int mode;                // 0: a + b (+ c)   1: avg_pool2(a) (a is [N][2H][2W][C])   2: b + bicubic_up2(a) (a is [N][H/2][W/2][C])
+                             // 3: relu(a * scale + shift), scale / shift = ss[n][c]   (a norm whose RESULT feeds another norm)
+    const float2 *ss;
 };
 
 __device__ __forceinline__ void cubic_w4(float t, float (&w)[4]) {     // torch upsample_bicubic2d, A = -0.75
@@ -154,6 +156,11 @@ __global__ void __launch_bounds__(256) k_ew_nhwc(const __grid_constant__ EwParam
                 const float4 c = *reinterpret_cast<const float4 *>(p.c + o);
                 v.x += c.x; v.y += c.y; v.z += c.z; v.w += c.w;
             }
+        } else if (p.mode == 3) {
+            v = *reinterpret_cast<const float4 *>(p.a + o);
+            const float2 *ss = p.ss + (size_t)n * p.C + q * 4;
+            v.x = fmaxf(fmaf(v.x, ss[0].x, ss[0].y), 0.f); v.y = fmaxf(fmaf(v.y, ss[1].x, ss[1].y), 0.f);
+            v.z = fmaxf(fmaf(v.z, ss[2].x, ss[2].y), 0.f); v.w = fmaxf(fmaf(v.w, ss[3].x, ss[3].y), 0.f);
         } else if (p.mode == 1) {
             const int oy = (int)(pix / p.W), ox = (int)(pix % p.W);
             const int W2 = 2 * p.W;
@@ -246,6 +253,48 @@ __global__ void k_nhwc_to_nchw(const float *__restrict__ x, float *__restrict__ 
     y[i] = x[((size_t)n * HW + pix) * Cs + c_off + c];
 }
 
+// ---------------------------------------------------------------------------------------- 7 x 7 stem operand
+// The encoders' first layer has 3..9 input channels: far too few for a 64-channel K-chunk per tap.  Instead the K axis
+// of the implicit GEMM runs over (kx, c) inside one filter ROW: with the image stored NHWC with C padded to Cp8 (8 or
+// 16), the 8 pixels x Cp8 channels a filter row touches are CONTIGUOUS in memory, so the operand of output pixel x is
+// the window starting at input pixel sx * x -- a tensor map whose W dimension has a stride of sx * Cp8 elements
+// (overlapping windows) lets the same TMA box load deliver it; the 8th pixel of the window meets zero weights.
+// x NCHW fp32 [N][Cin][H][W] -> hi / lo fp16 [N * sy][Hrows][Wp][Cp8] with a halo of 3 (reflection or zeros) and rows
+// split into sy parity planes (stride-2 stem: tap row ky reads plane ky % 2 at row offset ky / 2).
+__global__ void k_stem_pack(const float *__restrict__ x, __half *__restrict__ hi, __half *__restrict__ lo, int N, int Cin,
+                            int H, int W, int Cp8, int Wp, int Hrows, int sy, int reflect) {
+    const int64_t total = (int64_t)N * sy * Hrows * Wp;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int px = (int)(i % Wp);
+    int64_t r = i / Wp;
+    const int row = (int)(r % Hrows); r /= Hrows;
+    const int plane = (int)(r % sy);
+    const int n = (int)(r / sy);
+    const int py = row * sy + plane;                          // padded row
+    int sy_ = py - 3, sx_ = px - 3;
+    bool ok = py < H + 6 && px < W + 6;
+    if (reflect) {
+        sy_ = sy_ < 0 ? -sy_ : (sy_ >= H ? 2 * H - 2 - sy_ : sy_);
+        sx_ = sx_ < 0 ? -sx_ : (sx_ >= W ? 2 * W - 2 - sx_ : sx_);
+    } else {
+        ok = ok && sy_ >= 0 && sy_ < H && sx_ >= 0 && sx_ < W;
+    }
+    __half *dh = hi + (size_t)i * Cp8, *dl = lo + (size_t)i * Cp8;
+    for (int c0 = 0; c0 < Cp8; c0 += 8) {
+        __align__(16) __half h[8], l[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int c = c0 + k;
+            const float v = (ok && c < Cin) ? x[(((size_t)n * Cin + c) * H + sy_) * W + sx_] : 0.f;
+            h[k] = __float2half_rn(v);
+            l[k] = __float2half_rn(v - __half2float(h[k]));
+        }
+        *reinterpret_cast<uint4 *>(dh + c0) = *reinterpret_cast<const uint4 *>(h);
+        *reinterpret_cast<uint4 *>(dl + c0) = *reinterpret_cast<const uint4 *>(l);
+    }
+}
+
 // ---------------------------------------------------------------------------------------- 7 x 7 output head (Cout <= 3)
 // x fp32 NHWC [N][H][W][64], w torch layout [Cout][64][7][7], reflection pad 3, y NCHW [N][Cout][H][W], tanh optional
 __global__ void __launch_bounds__(128) k_conv7_head(const float *__restrict__ x, const float *__restrict__ w,
@@ -332,12 +381,13 @@ extern "C" int icon_act_nhwc(const float *x, int Cs_in, int ci_off, const float 
 extern "C" int icon_ew_nhwc(int mode, const float *a, const float *b, const float *c, float *y, double *stats, int N, int H,
                             int W, int C, icon_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    ICON_CHECK_ARG(a && y && N > 0 && H > 0 && W > 0 && mode >= 0 && mode <= 2, "icon_ew_nhwc: bad argument");
+    ICON_CHECK_ARG(a && y && N > 0 && H > 0 && W > 0 && mode >= 0 && mode <= 3, "icon_ew_nhwc: bad argument");
     ICON_CHECK_ARG(mode == 1 || b, "icon_ew_nhwc: second operand missing");
     ICON_CHECK_ARG(C % 4 == 0 && C <= 1024 && 256 % (C / 4) == 0, "icon_ew_nhwc: C=%d must be a power of two in [4, 1024]", C);
     ICON_CHECK_ARG(mode != 2 || (H % 2 == 0 && W % 2 == 0), "icon_ew_nhwc: upsample output must be even");
     EwParams p{};
-    p.a = a; p.b = b; p.c = c; p.y = y; p.stats = stats; p.N = N; p.H = H; p.W = W; p.C = C; p.mode = mode;
+    p.a = a; p.b = mode == 3 ? nullptr : b; p.c = c; p.y = y; p.stats = stats; p.N = N; p.H = H; p.W = W; p.C = C; p.mode = mode;
+    p.ss = mode == 3 ? (const float2 *)b : nullptr;
     dim3 grid((unsigned)(((int64_t)H * W + EW_PIX - 1) / EW_PIX), (unsigned)N);
     k_ew_nhwc<<<grid, 256, 2 * C * sizeof(float), stream>>>(p);
     ICON_LAUNCHED();
@@ -358,6 +408,19 @@ extern "C" int icon_nhwc_to_nchw(const float *x, float *y, int N, int C, int Cs,
     ICON_CHECK_ARG(x && y && N > 0 && C > 0 && c_off >= 0 && c_off + C <= Cs && HW > 0, "icon_nhwc_to_nchw: bad argument");
     const int64_t total = (int64_t)N * C * HW;
     k_nhwc_to_nchw<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(x, y, N, C, Cs, c_off, HW);
+    ICON_LAUNCHED();
+    return ICON_OK;
+}
+
+extern "C" int icon_stem_pack(const float *x, void *hi, void *lo, int N, int Cin, int H, int W, int Cp8, int Wp, int Hrows,
+                              int sy, int reflect, icon_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    ICON_CHECK_ARG(x && hi && lo && N > 0 && Cin > 0 && H > 3 && W > 3, "icon_stem_pack: bad argument");
+    ICON_CHECK_ARG((Cp8 == 8 || Cp8 == 16) && Cin <= Cp8 && (sy == 1 || sy == 2), "icon_stem_pack: Cin <= 16, stride 1 or 2");
+    ICON_CHECK_ARG(Wp >= W + 7 && Hrows * sy >= H + 6, "icon_stem_pack: padded extent too small");
+    const int64_t total = (int64_t)N * sy * Hrows * Wp;
+    k_stem_pack<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(x, (__half *)hi, (__half *)lo, N, Cin, H, W, Cp8, Wp, Hrows,
+                                                                    sy, reflect);
     ICON_LAUNCHED();
     return ICON_OK;
 }

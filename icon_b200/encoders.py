@@ -173,13 +173,11 @@ class HGFilter(nn.Module):
         return outputs
 
     def _forward_nhwc(self, x):
-        """HGFilters.py:161-197 on the NHWC / TMA / tcgen05 path (icon_b200/nhwc.py).  The 7x7 stride-2 stem (Cin = 3..9)
-        runs on the FP32 kernel in NCHW; everything after it is NHWC."""
-        C = _conv_ops()
+        """HGFilters.py:161-197 on the NHWC / TMA / tcgen05 path (icon_b200/nhwc.py), 7x7 stride-2 stem included."""
         from . import nhwc as T
         with torch.no_grad():
-            x = C.group_norm(C.conv2d(x, self.conv1), self.bn1, relu=True)      # NCHW, [N, 64, H/2, W/2]
-            x = T.raw_from_nchw(x)                                               # + statistics for conv2.bn1
+            r = T.stem_conv7(x, self.conv1, reflect=False)                       # 7x7 s2 on the tensor cores, [N,H/2,W/2,64]
+            x = T.norm_relu(r, T.finalize(r, self.bn1))                          # + statistics for conv2.bn1
             x = T.avg_pool2(self.conv2.forward_nhwc(x).dense())
             x = self.conv3.forward_nhwc(x)
             x = self.conv4.forward_nhwc(x)
@@ -277,13 +275,13 @@ class GlobalGenerator(nn.Module):
     def _forward_nhwc(self, x):
         """FBNet.py:216-264 on the NHWC / TMA / tcgen05 path: every InstanceNorm reads the sums its producing conv
         accumulated; ReflectionPad2d = halo written by the normalising pass; stride-2 convs read space-to-depth
-        planes; ConvTranspose2d = 4 output phases.  Stem (Cin = 6) on the FP32 kernel in NCHW, head on k_conv7_head."""
-        C = _conv_ops()
+        planes; ConvTranspose2d = 4 output phases; the 7x7 stem (Cin = 6) runs its K axis over filter rows; the 64 -> 3
+        head is FP32 (k_conv7_head)."""
         from . import nhwc as T
         m = self.model
         nd, nb = self.n_downsampling, self.n_blocks
         with torch.no_grad():
-            raw = T.raw_from_nchw(C.conv2d(x, m[1], reflect=3))
+            raw = T.stem_conv7(x, m[1], reflect=True)
             idx = 4
             for _ in range(nd):
                 op, _ = T.act(raw, T.finalize(raw), relu=True, s2d=True)

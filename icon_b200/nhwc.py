@@ -246,6 +246,55 @@ def conv(op, m, out=None, co_off=0, stats=True):
     return Raw(out, C=Cout, c_off=co_off, stats=st)
 
 
+def stem_conv7(x, m, reflect, stats=True):
+    """The encoders' first layer -- [ReflectionPad2d(3) +] Conv2d(Cin <= 16, Cout, 7, stride 1 | 2, zero padding 3 when
+    not reflect) -- from the NCHW fp32 network input to a Raw NHWC output, on the tensor cores: K runs over the
+    8 pixels x Cp8 channels of a filter row (contiguous in the packed operand, csrc/act_nhwc.cu k_stem_pack), so a
+    tap row is one (Cp8 = 8) or two (Cp8 = 16) 64-wide K-chunks and the layer is 7 taps of the generic kernel."""
+    _need_cuda(x)
+    x = x.detach().float().contiguous()
+    N, Cin, H, W = x.shape
+    w = m.weight
+    Cout, _, KH, KW = w.shape
+    s = m.stride[0]
+    if (KH, KW) != (7, 7) or Cin > 16 or s not in (1, 2) or w.shape[1] != Cin or (not reflect and m.padding[0] != 3):
+        raise NotImplementedError("stem_conv7: 7x7, Cin <= 16, stride 1 or 2, padding 3 (reflect or zero)")
+    dev = x.device
+    Cp8 = 8 if Cin <= 8 else 16
+    OH, OW = (H + 6 - 7) // s + 1, (W + 6 - 7) // s + 1
+    Wp = ((OW - 1) * s + 8 + 7) // 8 * 8
+    Wp = max(Wp, (W + 7 + 7) // 8 * 8)
+    Hrows = (H + 6 + s - 1) // s
+    hi = torch.empty(N * s, Hrows, Wp, Cp8, dtype=torch.float16, device=dev)
+    lo = torch.empty_like(hi)
+    check(lib.icon_stem_pack(_p(x), _p(hi), _p(lo), N, Cin, H, W, Cp8, Wp, Hrows, s, 1 if reflect else 0, _stream()),
+          "icon_stem_pack")
+    cpt = Cp8 // 8                                              # 64-wide chunks per tap row
+    n_tile = _n_tile(Cout)
+    key = (w.data_ptr(), w._version, str(w.device), "stem", Cp8, n_tile)
+    cache = m.__dict__.setdefault("_icon_pack", {})
+    blob = cache.get(key)
+    if blob is None:
+        wk = torch.zeros(Cout, 7, 8, Cp8, dtype=torch.float32, device=w.device)      # [co][ky][kx (8th = 0)][c]
+        wk[:, :, :7, :Cin] = w.detach().float().permute(0, 2, 3, 1)
+        blob = pack_tiles(wk.reshape(Cout, 7 * 8 * Cp8), n_tile)
+        for k in [k for k in cache if k[:3] != key[:3]]:
+            del cache[k]
+        cache[key] = blob
+    out = torch.empty(N, OH, OW, Cout, dtype=torch.float32, device=dev)
+    st = new_stats(N, Cout, dev) if stats else None
+    bias = m.bias.detach().float().contiguous() if m.bias is not None else None
+    taps = [(ky // s, 0, ky % s, ky) for ky in range(7)]
+    dims = (ctypes.c_int64 * 4)(8 * Cp8, OW, Hrows, N * s)
+    strides = (ctypes.c_int64 * 3)(s * Cp8, Wp * Cp8, Hrows * Wp * Cp8)
+    flat = [int(v) for t in taps for v in t]
+    tap_arr = (ctypes.c_int * len(flat))(*flat)
+    check(lib.icon_conv_nhwc(_p(hi), _p(lo), dims, strides, _p(blob), 7 * cpt, _p(bias), _p(out), OH, OW, Cout, 0, Cout, N,
+                             OH, OW, 1, 1, 0, 0, s, 7, tap_arr, cpt, n_tile, 1, _p(st), None, 0, _stream()),
+          "icon_conv_nhwc(stem)")
+    return Raw(out, stats=st)
+
+
 def conv_transpose(op, m, stats=True):
     """nn.ConvTranspose2d(k, stride 2, padding, output_padding) as 4 output phases, each a stride-1 gather over the
     input with the taps of matching parity (FBNet.py:245-252: k3, s2, p1, op1 -> 1 / 2 / 2 / 4 taps)."""
@@ -304,6 +353,12 @@ def bicubic_up2_add(low, up, stats=True):
     if tuple(low.shape) != (N, H // 2, W // 2, C):
         raise _C.IconError("bicubic_up2_add: shape mismatch")
     return _ew(2, low, up, None, N, H, W, C, stats)
+
+
+def norm_relu(raw, ss, stats=True):
+    """relu(x * scale + shift) as fp32 NHWC WITH the statistics of the result: a normalisation whose output is read
+    by another normalisation (HGFilter: relu(bn1(conv1(x))) feeds conv2.bn1, HGFilters.py:162-164)."""
+    return _ew(3, raw.dense(), ss, None, raw.N, raw.H, raw.W, raw.C, stats)
 
 
 def conv7_head(x_f32, m, tanh):

@@ -230,7 +230,8 @@ int icon_conv2d_tc(const float *x, const void *wt_packed, const float *bias, con
  * icon_norm_finalize: stats -> [N][C] (scale, shift) for InstanceNorm2d (groups = 0) / GroupNorm(groups) with affine.
  * icon_act_nhwc: y = [relu](x * scale + shift) [+ res]  -> hi / lo operand tensors (halo > 0: reflection halo;
  *   s2d = 1: four parity planes for a stride-2 consumer; channels padded to Cp with zeros) and / or fp32 NHWC.
- * icon_ew_nhwc: mode 0 a + b (+ c), 1 avg_pool2(a), 2 b + bicubic_up2(a, align_corners); optional stats of the result.
+ * icon_ew_nhwc: mode 0 a + b (+ c), 1 avg_pool2(a), 2 b + bicubic_up2(a, align_corners), 3 relu(a * scale + shift) with
+ *   b = the [N][C] (scale, shift) table of icon_norm_finalize; optional stats of the result.
  * icon_nchw_to_nhwc / icon_nhwc_to_nchw: layout adaptors (the former with optional stats).
  * icon_conv7_head: 7 x 7 reflection-padded 64 -> (1..3) channel convolution from fp32 NHWC to NCHW, act 2 = tanh. */
 size_t icon_conv_nhwc_workspace_bytes(int N, int Ht, int Wt, int Cout, int splits);
@@ -246,6 +247,12 @@ int icon_ew_nhwc(int mode, const float *a, const float *b, const float *c, float
                  int C, icon_stream_t stream);
 int icon_nchw_to_nhwc(const float *x, float *y, double *stats, int N, int C, int64_t HW, icon_stream_t stream);
 int icon_nhwc_to_nchw(const float *x, float *y, int N, int C, int Cs, int c_off, int64_t HW, icon_stream_t stream);
+/* icon_stem_pack: NCHW fp32 image -> hi / lo fp16 [N * sy][Hrows][Wp][Cp8] (Cp8 = 8 | 16 >= Cin) with a 3-pixel halo
+ * (reflect = 1: ReflectionPad2d(3); 0: zeros) and rows split into sy parity planes: the operand layout of the 7 x 7
+ * first layers (K runs over the 8 x Cp8 contiguous values of a filter row; icon_conv_nhwc reads it through a tensor
+ * map whose W stride is sx * Cp8 elements). */
+int icon_stem_pack(const float *x, void *hi, void *lo, int N, int Cin, int H, int W, int Cp8, int Wp, int Hrows, int sy,
+                   int reflect, icon_stream_t stream);
 int icon_conv7_head(const float *x, const float *w, const float *bias, float *y, int N, int H, int W, int Cin, int Cout,
                     int act, icon_stream_t stream);
 /* ---- clean_mesh (csrc/clean.cu; reference lib/dataset/mesh_util.py:778-791: trimesh split + largest component).

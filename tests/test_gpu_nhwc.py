@@ -193,3 +193,37 @@ def test_packed_weights_follow_weight_updates_and_invalidate_hook():
     T.invalidate_packed(conv)                        # ... the documented hook drops the blobs
     y3 = T.to_nchw(T.conv(op, conv, stats=False))
     assert torch.allclose(y3, y1, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("cin,stride,reflect,h,w", [(6, 1, True, 64, 48), (3, 2, False, 64, 64), (9, 2, False, 32, 80),
+                                                    (6, 1, True, 512, 512)])
+def test_stem_conv7_on_tensor_cores(cin, stride, reflect, h, w):
+    """First layers: ReflectionPad2d(3) + Conv2d(6, 64, 7) (FBNet.py:216-218) and Conv2d(3 | 9, 64, 7, stride 2,
+    padding 3) (HGFilters.py:95-107), K running over filter rows."""
+    dev = _cuda()
+    from icon_b200 import nhwc as T
+    conv = nn.Conv2d(cin, 64, 7, stride=stride, padding=0 if reflect else 3)
+    x = torch.randn(1, cin, h, w, generator=_g(cin + h))
+    with torch.no_grad():
+        ref = conv(F.pad(x, (3, 3, 3, 3), mode="reflect") if reflect else x)
+    out = T.stem_conv7(x.to(dev), conv.to(dev), reflect=reflect)
+    y = T.to_nchw(out).cpu()
+    assert y.shape == ref.shape
+    assert (y - ref).abs().max() <= _tol(ref)
+    assert torch.allclose(out.stats.cpu()[..., 0], ref.double().sum(dim=(2, 3)), rtol=1e-5, atol=1e-2)
+
+
+def test_norm_relu_with_statistics_of_the_result():
+    dev = _cuda()
+    from icon_b200 import nhwc as T
+    x = torch.randn(2, 64, 16, 24, generator=_g(11)) * 2 + 0.7
+    m = nn.GroupNorm(32, 64)
+    with torch.no_grad():
+        m.weight.copy_(1 + 0.1 * torch.randn(64, generator=_g(3)))
+        m.bias.copy_(0.1 * torch.randn(64, generator=_g(4)))
+        ref = F.relu(m(x))
+    raw = T.raw_from_nchw(x.to(dev))
+    r = T.norm_relu(raw, T.finalize(raw, m.to(dev)))
+    assert (T.to_nchw(r).cpu() - ref).abs().max() <= 3e-5
+    assert torch.allclose(r.stats.cpu()[..., 0], ref.double().sum(dim=(2, 3)), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(r.stats.cpu()[..., 1], (ref.double() ** 2).sum(dim=(2, 3)), rtol=1e-4, atol=1e-2)
