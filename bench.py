@@ -378,8 +378,8 @@ def recon_stage(dev, cfg, netG, wl, rank, world, reps=3):
                 "verts_rank0_image": int(verts.shape[0]), "faces_rank0_image": int(faces.shape[0]),
                 "images_gathered": len(got) if rank == 0 else None,
                 "gather_payload_bytes": int(nbytes),
-                "gather": "all_gather(headers) + grouped ncclSend/ncclRecv of verts/faces to rank 0" if world > 1
-                          else "single rank: no collective",
+                "gather_how": "all_gather(headers) + grouped ncclSend/ncclRecv of verts/faces to rank 0" if world > 1
+                              else "single rank: no collective",
                 "ms_per_image_device": out["filter"] + out["engine"] + out["marching_cubes"]})
     if rank == 0 and host:
         out["verts_total"] = int(sum(v.shape[0] for v, _ in host))

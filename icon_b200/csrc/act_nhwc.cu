@@ -134,13 +134,13 @@ __device__ __forceinline__ void cubic_w4(float t, float (&w)[4]) {     // torch 
 constexpr int EW_PIX = 256;          // pixels per block
 // grid (ceil(H*W / EW_PIX), N), 256 threads: thread = (channel quad, pixel row); C % 4 == 0, C / 4 divides 256
 __global__ void __launch_bounds__(256) k_ew_nhwc(const __grid_constant__ EwParams p) {
-    extern __shared__ float sacc[];                            // [C][2]
+    extern __shared__ double sacc[];                           // [C][2]; fp64 so that the atomic order cannot show in fp32
     const int quads = p.C / 4, rows = 256 / quads;
     const int q = threadIdx.x % quads, r0 = threadIdx.x / quads;
     const int n = blockIdx.y;
     const int64_t hw = (int64_t)p.H * p.W;
     const int64_t pix0 = (int64_t)blockIdx.x * EW_PIX;
-    for (int i = threadIdx.x; i < 2 * p.C; i += 256) sacc[i] = 0.f;
+    for (int i = threadIdx.x; i < 2 * p.C; i += 256) sacc[i] = 0.0;
     __syncthreads();
     float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
     for (int pr = r0; pr < EW_PIX; pr += rows) {
@@ -203,26 +203,28 @@ __global__ void __launch_bounds__(256) k_ew_nhwc(const __grid_constant__ EwParam
         s2.x = fmaf(v.x, v.x, s2.x); s2.y = fmaf(v.y, v.y, s2.y); s2.z = fmaf(v.z, v.z, s2.z); s2.w = fmaf(v.w, v.w, s2.w);
     }
     if (!p.stats) return;
-    atomicAdd(&sacc[(q * 4 + 0) * 2], s1.x); atomicAdd(&sacc[(q * 4 + 0) * 2 + 1], s2.x);
-    atomicAdd(&sacc[(q * 4 + 1) * 2], s1.y); atomicAdd(&sacc[(q * 4 + 1) * 2 + 1], s2.y);
-    atomicAdd(&sacc[(q * 4 + 2) * 2], s1.z); atomicAdd(&sacc[(q * 4 + 2) * 2 + 1], s2.z);
-    atomicAdd(&sacc[(q * 4 + 3) * 2], s1.w); atomicAdd(&sacc[(q * 4 + 3) * 2 + 1], s2.w);
+    atomicAdd(&sacc[(q * 4 + 0) * 2], (double)s1.x); atomicAdd(&sacc[(q * 4 + 0) * 2 + 1], (double)s2.x);
+    atomicAdd(&sacc[(q * 4 + 1) * 2], (double)s1.y); atomicAdd(&sacc[(q * 4 + 1) * 2 + 1], (double)s2.y);
+    atomicAdd(&sacc[(q * 4 + 2) * 2], (double)s1.z); atomicAdd(&sacc[(q * 4 + 2) * 2 + 1], (double)s2.z);
+    atomicAdd(&sacc[(q * 4 + 3) * 2], (double)s1.w); atomicAdd(&sacc[(q * 4 + 3) * 2 + 1], (double)s2.w);
     __syncthreads();
-    for (int i = threadIdx.x; i < 2 * p.C; i += 256) atomicAdd(p.stats + (size_t)n * p.C * 2 + i, (double)sacc[i]);
+    for (int i = threadIdx.x; i < 2 * p.C; i += 256) atomicAdd(p.stats + (size_t)n * p.C * 2 + i, sacc[i]);
 }
 
 // ---------------------------------------------------------------------------------------- layout adaptors
-// x [N][C][HW] -> y [N][HW][C] (+ stats).  grid (ceil(HW / 32), N), 256 threads, C <= 256.
+// x [N][C][HW] -> y [N][HW][C] (+ stats).  grid (ceil(HW / 32), N, ceil(C / 256)), 256 threads.
 __global__ void __launch_bounds__(256) k_nchw_to_nhwc(const float *__restrict__ x, float *__restrict__ y,
                                                       double *__restrict__ stats, int C, int64_t HW) {
-    extern __shared__ float tile[];                            // [32][C + 1]
+    extern __shared__ float tile[];                            // [32][CB + 1]
     const int n = blockIdx.y;
+    const int cb0 = blockIdx.z * 256, CB = min(256, C - cb0);
     const int64_t p0 = (int64_t)blockIdx.x * 32;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (int c = w; c < C; c += 8) {
+    for (int cc = w; cc < CB; cc += 8) {
+        const int c = cb0 + cc;
         const int64_t pix = p0 + lane;
         const float v = pix < HW ? x[((size_t)n * C + c) * HW + pix] : 0.f;
-        tile[lane * (C + 1) + c] = v;
+        tile[lane * (CB + 1) + cc] = v;
         if (stats) {
             float s1 = v, s2 = v * v;
 #pragma unroll
@@ -238,9 +240,9 @@ __global__ void __launch_bounds__(256) k_nchw_to_nhwc(const float *__restrict__ 
     }
     __syncthreads();
     const int64_t npx = min((int64_t)32, HW - p0);
-    for (int i = threadIdx.x; i < npx * C; i += 256) {
-        const int px = i / C, c = i % C;
-        y[((size_t)n * HW + p0) * C + i] = tile[px * (C + 1) + c];
+    for (int i = threadIdx.x; i < npx * CB; i += 256) {
+        const int px = i / CB, cc = i % CB;
+        y[((size_t)n * HW + p0 + px) * C + cb0 + cc] = tile[px * (CB + 1) + cc];
     }
 }
 
@@ -389,16 +391,16 @@ extern "C" int icon_ew_nhwc(int mode, const float *a, const float *b, const floa
     p.a = a; p.b = mode == 3 ? nullptr : b; p.c = c; p.y = y; p.stats = stats; p.N = N; p.H = H; p.W = W; p.C = C; p.mode = mode;
     p.ss = mode == 3 ? (const float2 *)b : nullptr;
     dim3 grid((unsigned)(((int64_t)H * W + EW_PIX - 1) / EW_PIX), (unsigned)N);
-    k_ew_nhwc<<<grid, 256, 2 * C * sizeof(float), stream>>>(p);
+    k_ew_nhwc<<<grid, 256, 2 * C * sizeof(double), stream>>>(p);
     ICON_LAUNCHED();
     return ICON_OK;
 }
 
 extern "C" int icon_nchw_to_nhwc(const float *x, float *y, double *stats, int N, int C, int64_t HW, icon_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    ICON_CHECK_ARG(x && y && N > 0 && C > 0 && C <= 256 && HW > 0, "icon_nchw_to_nhwc: bad argument (C <= 256)");
-    dim3 grid((unsigned)((HW + 31) / 32), (unsigned)N);
-    k_nchw_to_nhwc<<<grid, 256, 32 * (C + 1) * sizeof(float), stream>>>(x, y, stats, C, HW);
+    ICON_CHECK_ARG(x && y && N > 0 && C > 0 && HW > 0, "icon_nchw_to_nhwc: bad argument");
+    dim3 grid((unsigned)((HW + 31) / 32), (unsigned)N, (unsigned)((C + 255) / 256));
+    k_nchw_to_nhwc<<<grid, 256, 32 * (min(C, 256) + 1) * sizeof(float), stream>>>(x, y, stats, C, HW);
     ICON_LAUNCHED();
     return ICON_OK;
 }

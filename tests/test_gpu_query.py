@@ -144,7 +144,10 @@ def test_query_func_on_real_scan_body_matches_oracle(mlp_impl, golden_dir):
     with torch.no_grad():
         out = net.query_func(cfg, netG, [feat.to(dev)], pts.to(dev)).cpu()
     ref = OQ.query_func(sd, [feat], pts, prior="icon", smpl=smpl, sdf_clip=0.05)
-    assert (out - ref).abs().max() <= 1e-4
+    # sliver faces blow the UNCLAMPED plane-projection barycentrics up (mesh_util.py:337-353), so cmap / normal
+    # features -- and with them the logits -- reach 1e2..1e4 on this mesh, in the reference as much as here: the
+    # 1e-4 bar is on the logit scale O(1), elsewhere it is relative
+    assert ((out - ref).abs() / ref.abs().clamp(min=1.0)).max() <= 1e-4, (ref.abs().max().item(), (out - ref).abs().max().item())
 
 
 @pytest.mark.parametrize("ppw", [1, 8, 32])
