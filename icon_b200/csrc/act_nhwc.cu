@@ -46,7 +46,12 @@ __global__ void k_norm_finalize(const double *__restrict__ stats, const float *_
 // ---------------------------------------------------------------------------------------- normalise + split
 struct ActParams {
     const float *x;          // fp32 NHWC [N][H][W][Cs_in], channels [ci_off, ci_off + C)
-    const float2 *ss;        // [N][C] scale / shift or null (identity)
+    const float2 *ss;        // [N][C] scale / shift or null
+    const double *stats;     // or: [N][C][2] sums straight from the producer (normalisation folded in here); both null =
+    const float *gamma, *beta;   // identity.  gamma / beta: GroupNorm affine or null
+    int cg;                  // channels per normalisation group (1 = instance norm), 8 % cg == 0
+    double inv_count;        // 1 / (pixels * cg)
+    float eps;
     const float *res;        // fp32 NHWC [N][H][W][C] or null: added AFTER the activation
     __half *hi, *lo;         // [N * planes][Hp][Wp][Cp] or null
     float *f32;              // fp32 NHWC [N][H][W][C] or null
@@ -75,22 +80,62 @@ __global__ void k_act_nhwc(const __grid_constant__ ActParams p) {
     const int c0 = g * 8;
     float v[8];
     const size_t spix = ((size_t)n * p.H + sy) * p.W + sx;
+    const float *xs = p.x + spix * p.Cs_in + p.ci_off + c0;
+    if (c0 + 8 <= p.C && ((reinterpret_cast<uintptr_t>(xs) & 15) == 0)) {            // 2 x 128-bit loads
+        const float4 a = *reinterpret_cast<const float4 *>(xs), b = *reinterpret_cast<const float4 *>(xs + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int c = c0 + k;
-        float y = 0.f;
-        if (c < p.C) {
-            y = p.x[spix * p.Cs_in + p.ci_off + c];
-            if (p.ss) { const float2 s = __ldg(p.ss + (size_t)n * p.C + c); y = fmaf(y, s.x, s.y); }
-            if (p.relu) y = fmaxf(y, 0.f);
-            if (p.res) y += p.res[spix * p.C + c];
-        }
-        v[k] = y;
+        for (int k = 0; k < 8; ++k) v[k] = (c0 + k < p.C) ? xs[k] : 0.f;
     }
-    if (p.f32 && interior) {
+    if (p.ss) {
+        const float2 *ss = p.ss + (size_t)n * p.C + c0;
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-            if (c0 + k < p.C) p.f32[spix * p.C + c0 + k] = v[k];
+            if (c0 + k < p.C) { const float2 s = __ldg(ss + k); v[k] = fmaf(v[k], s.x, s.y); }
+    } else if (p.stats) {
+        // scale / shift from the producer's sums: a thread's 8 channels hold whole groups (cg in {1, 2, 4, 8})
+        const double *st = p.stats + ((size_t)n * p.C + c0) * 2;
+        for (int g0 = 0; g0 < 8; g0 += p.cg) {
+            if (c0 + g0 >= p.C) break;
+            double s = 0.0, q = 0.0;
+            for (int k = 0; k < p.cg; ++k) { s += st[(g0 + k) * 2]; q += st[(g0 + k) * 2 + 1]; }
+            const double mean = s * p.inv_count;
+            const float var = fmaxf((float)(q * p.inv_count - mean * mean), 0.f);
+            const float rstd = rsqrtf(var + p.eps);
+            for (int k = 0; k < p.cg; ++k) {
+                const int c = c0 + g0 + k;
+                const float ga = p.gamma ? __ldg(p.gamma + c) : 1.f, be = p.beta ? __ldg(p.beta + c) : 0.f;
+                const float sc = rstd * ga;
+                v[g0 + k] = fmaf(v[g0 + k], sc, be - (float)mean * sc);
+            }
+        }
+    }
+    if (p.relu) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
+    }
+    if (p.res) {
+        const float *rs = p.res + spix * p.C + c0;
+        if (c0 + 8 <= p.C && ((reinterpret_cast<uintptr_t>(rs) & 15) == 0)) {
+            const float4 a = *reinterpret_cast<const float4 *>(rs), b = *reinterpret_cast<const float4 *>(rs + 4);
+            v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (c0 + k < p.C) v[k] += rs[k];
+        }
+    }
+    if (p.f32 && interior) {
+        float *fd = p.f32 + spix * p.C + c0;
+        if (c0 + 8 <= p.C && ((reinterpret_cast<uintptr_t>(fd) & 15) == 0)) {
+            *reinterpret_cast<float4 *>(fd) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4 *>(fd + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (c0 + k < p.C) fd[k] = v[k];
+        }
     }
     if (p.hi) {
         size_t d;
@@ -131,17 +176,15 @@ __device__ __forceinline__ void cubic_w4(float t, float (&w)[4]) {     // torch 
     x = 2.f - t; w[3] = ((A * x - 5.f * A) * x + 8.f * A) * x - 4.f * A;
 }
 
-constexpr int EW_PIX = 256;          // pixels per block
+constexpr int EW_PIX = 64;           // pixels per block
 // grid (ceil(H*W / EW_PIX), N), 256 threads: thread = (channel quad, pixel row); C % 4 == 0, C / 4 divides 256
 __global__ void __launch_bounds__(256) k_ew_nhwc(const __grid_constant__ EwParams p) {
-    extern __shared__ double sacc[];                           // [C][2]; fp64 so that the atomic order cannot show in fp32
+    __shared__ float sred[2][256 * 4];                         // [sum | sum of squares][row][channel]: rows * C = 1024
     const int quads = p.C / 4, rows = 256 / quads;
     const int q = threadIdx.x % quads, r0 = threadIdx.x / quads;
     const int n = blockIdx.y;
     const int64_t hw = (int64_t)p.H * p.W;
     const int64_t pix0 = (int64_t)blockIdx.x * EW_PIX;
-    for (int i = threadIdx.x; i < 2 * p.C; i += 256) sacc[i] = 0.0;
-    __syncthreads();
     float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
     for (int pr = r0; pr < EW_PIX; pr += rows) {
         const int64_t pix = pix0 + pr;
@@ -203,12 +246,16 @@ __global__ void __launch_bounds__(256) k_ew_nhwc(const __grid_constant__ EwParam
         s2.x = fmaf(v.x, v.x, s2.x); s2.y = fmaf(v.y, v.y, s2.y); s2.z = fmaf(v.z, v.z, s2.z); s2.w = fmaf(v.w, v.w, s2.w);
     }
     if (!p.stats) return;
-    atomicAdd(&sacc[(q * 4 + 0) * 2], (double)s1.x); atomicAdd(&sacc[(q * 4 + 0) * 2 + 1], (double)s2.x);
-    atomicAdd(&sacc[(q * 4 + 1) * 2], (double)s1.y); atomicAdd(&sacc[(q * 4 + 1) * 2 + 1], (double)s2.y);
-    atomicAdd(&sacc[(q * 4 + 2) * 2], (double)s1.z); atomicAdd(&sacc[(q * 4 + 2) * 2 + 1], (double)s2.z);
-    atomicAdd(&sacc[(q * 4 + 3) * 2], (double)s1.w); atomicAdd(&sacc[(q * 4 + 3) * 2 + 1], (double)s2.w);
+    // per-channel sums of the block in a fixed order (row 0, 1, ...): deterministic, no shared-memory atomics
+    *reinterpret_cast<float4 *>(&sred[0][r0 * p.C + q * 4]) = s1;
+    *reinterpret_cast<float4 *>(&sred[1][r0 * p.C + q * 4]) = s2;
     __syncthreads();
-    for (int i = threadIdx.x; i < 2 * p.C; i += 256) atomicAdd(p.stats + (size_t)n * p.C * 2 + i, sacc[i]);
+    for (int i = threadIdx.x; i < 2 * p.C; i += 256) {
+        const int w = i / p.C, c = i - w * p.C;
+        double t = 0.0;
+        for (int r = 0; r < rows; ++r) t += (double)sred[w][r * p.C + c];
+        atomicAdd(p.stats + ((size_t)n * p.C + c) * 2 + w, t);
+    }
 }
 
 // ---------------------------------------------------------------------------------------- layout adaptors
@@ -347,9 +394,48 @@ __global__ void __launch_bounds__(128) k_conv7_head(const float *__restrict__ x,
     }
 }
 
+// out[n][co][y][x] = act(bias[co] + sum_{ky,kx} P[n][refl(y + ky - 3)][refl(x + kx - 3)][(ky * 7 + kx) * Cout + co])
+// P = the 1 x 1 tensor-core GEMM of the 64-channel activation with the head's weights regrouped per tap
+// (49 * Cout columns): the 7 x 7 head (FBNet.py:258-261) as GEMM + col2im instead of an N = 3 implicit GEMM.
+__global__ void __launch_bounds__(256) k_col2im7(const float *__restrict__ P, const float *__restrict__ bias,
+                                                 float *__restrict__ y, int N, int H, int W, int Cout, int Ps, int act) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)N * H * W) return;
+    const int ox = (int)(i % W), oy = (int)((i / W) % H), n = (int)(i / ((int64_t)W * H));
+    float acc[3] = {0.f, 0.f, 0.f};
+    for (int ky = 0; ky < 7; ++ky) {
+        int iy = oy + ky - 3;
+        iy = iy < 0 ? -iy : (iy >= H ? 2 * H - 2 - iy : iy);
+        const float *row = P + ((size_t)n * H + iy) * W * Ps;
+#pragma unroll
+        for (int kx = 0; kx < 7; ++kx) {
+            int ix = ox + kx - 3;
+            ix = ix < 0 ? -ix : (ix >= W ? 2 * W - 2 - ix : ix);
+            const float *s = row + (size_t)ix * Ps + (ky * 7 + kx) * Cout;
+            for (int co = 0; co < Cout; ++co) acc[co] += __ldg(s + co);
+        }
+    }
+    for (int co = 0; co < Cout; ++co) {
+        float v = acc[co] + (bias ? bias[co] : 0.f);
+        if (act == 2) v = tanhf(v);
+        else if (act == 1) v = fmaxf(v, 0.f);
+        y[(((size_t)n * Cout + co) * H + oy) * W + ox] = v;
+    }
+}
+
 }  // namespace icon
 
 using namespace icon;
+
+extern "C" int icon_col2im7(const float *P, const float *bias, float *y, int N, int H, int W, int Cout, int Ps, int act,
+                            icon_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    ICON_CHECK_ARG(P && y && N > 0 && H > 3 && W > 3 && Cout >= 1 && Cout <= 3 && Ps >= 49 * Cout, "icon_col2im7: bad argument");
+    const int64_t total = (int64_t)N * H * W;
+    k_col2im7<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(P, bias, y, N, H, W, Cout, Ps, act);
+    ICON_LAUNCHED();
+    return ICON_OK;
+}
 
 extern "C" int icon_norm_finalize(const double *stats, const float *gamma, const float *beta, float *scale_shift, int N, int C,
                                   int groups, double count, float eps, icon_stream_t stream_) {
@@ -362,7 +448,8 @@ extern "C" int icon_norm_finalize(const double *stats, const float *gamma, const
     return ICON_OK;
 }
 
-extern "C" int icon_act_nhwc(const float *x, int Cs_in, int ci_off, const float *scale_shift, const float *res, void *hi,
+extern "C" int icon_act_nhwc(const float *x, int Cs_in, int ci_off, const float *scale_shift, const double *stats,
+                             const float *gamma, const float *beta, int groups, float eps, const float *res, void *hi,
                              void *lo, float *f32, int N, int H, int W, int C, int Cp, int halo, int s2d, int relu,
                              icon_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
@@ -371,7 +458,16 @@ extern "C" int icon_act_nhwc(const float *x, int Cs_in, int ci_off, const float 
     ICON_CHECK_ARG(!s2d || (halo == 0 && H % 2 == 0 && W % 2 == 0), "icon_act_nhwc: space-to-depth needs even H, W and no halo");
     ICON_CHECK_ARG(halo >= 0 && halo < H && halo < W, "icon_act_nhwc: reflection halo %d needs halo < H, W", halo);
     ICON_CHECK_ARG(ci_off >= 0 && ci_off + C <= Cs_in, "icon_act_nhwc: channel slice outside the input tensor");
+    ICON_CHECK_ARG(!(scale_shift && stats), "icon_act_nhwc: scale_shift and stats are exclusive");
+    ICON_CHECK_ARG((gamma == nullptr) == (beta == nullptr), "icon_act_nhwc: gamma and beta go together");
     ActParams p{};
+    p.stats = stats; p.gamma = gamma; p.beta = beta; p.eps = eps; p.cg = 1; p.inv_count = 1.0 / ((double)H * W);
+    if (stats && groups > 0) {
+        ICON_CHECK_ARG(C % groups == 0, "icon_act_nhwc: C %% groups != 0");
+        p.cg = C / groups;
+        ICON_CHECK_ARG(p.cg == 1 || p.cg == 2 || p.cg == 4 || p.cg == 8, "icon_act_nhwc: %d channels per group (use icon_norm_finalize)", p.cg);
+        p.inv_count = 1.0 / ((double)H * W * p.cg);
+    }
     p.x = x; p.ss = (const float2 *)scale_shift; p.res = res; p.hi = (__half *)hi; p.lo = (__half *)lo; p.f32 = f32;
     p.N = N; p.H = H; p.W = W; p.C = C; p.Cs_in = Cs_in; p.ci_off = ci_off; p.Cp = Cp; p.P = halo; p.s2d = s2d; p.relu = relu;
     const int64_t total = (int64_t)N * (s2d ? H : H + 2 * halo) * (s2d ? W : W + 2 * halo) * (Cp / 8);
@@ -391,7 +487,7 @@ extern "C" int icon_ew_nhwc(int mode, const float *a, const float *b, const floa
     p.a = a; p.b = mode == 3 ? nullptr : b; p.c = c; p.y = y; p.stats = stats; p.N = N; p.H = H; p.W = W; p.C = C; p.mode = mode;
     p.ss = mode == 3 ? (const float2 *)b : nullptr;
     dim3 grid((unsigned)(((int64_t)H * W + EW_PIX - 1) / EW_PIX), (unsigned)N);
-    k_ew_nhwc<<<grid, 256, 2 * C * sizeof(double), stream>>>(p);
+    k_ew_nhwc<<<grid, 256, 0, stream>>>(p);
     ICON_LAUNCHED();
     return ICON_OK;
 }

@@ -210,58 +210,31 @@ k_conv_nhwc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ 
     }
 }
 
-// out = sum_s partial[s] + bias, + per-(image, channel) statistics.  Block: 128 logical pixels x 32 channels.
+// out = bias + sum_s partial[s], + per-(image, channel) statistics.  One thread per channel (coalesced across the
+// block), 32 logical pixels per block, fixed summation order (deterministic).  grid (ceil(HW / 32), ceil(Cout / 128), N).
+constexpr int SK_PIX = 32;
 __global__ void __launch_bounds__(128) k_splitk_nhwc(const __grid_constant__ ConvNhwcParams p) {
-    __shared__ float red[128 * 33];
-    __shared__ float part[4 * 32 * 2];
-    const int64_t hw = (int64_t)p.Ht * p.Wt;
+    const int c = blockIdx.y * 128 + threadIdx.x;
+    if (c >= p.Cout) return;
     const int n = blockIdx.z;
-    const int64_t pix = (int64_t)blockIdx.x * 128 + threadIdx.x;
-    const int c0 = blockIdx.y * 32;
-    const bool pv = pix < hw;
-    const int a = pv ? (int)(pix / p.Wt) : 0, b = pv ? (int)(pix % p.Wt) : 0;
-    float v[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = 0.f;
-    if (pv) {
-        for (int s = 0; s < p.splits; ++s) {
-            const float *src = p.partial + ((((size_t)s * p.N + n) * p.Ht + a) * p.Wt + b) * p.Cout + c0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-                if (c0 + j < p.Cout) v[j] += src[j];
-        }
-        float *dst = p.out + (((size_t)n * p.OHf + (size_t)(a * p.osy + p.ooy)) * p.OWf + (size_t)(b * p.osx + p.oox)) * p.Cs +
-                     p.co_off + c0;
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-            if (c0 + j < p.Cout) {
-                if (p.bias) v[j] += __ldg(p.bias + c0 + j);
-                dst[j] = v[j];
-            }
+    const int64_t hw = (int64_t)p.Ht * p.Wt;
+    const int64_t pix0 = (int64_t)blockIdx.x * SK_PIX;
+    const float bias = p.bias ? __ldg(p.bias + c) : 0.f;
+    const size_t split_stride = (size_t)p.N * hw * p.Cout;
+    float s1 = 0.f, s2 = 0.f;
+    for (int i = 0; i < SK_PIX; ++i) {
+        const int64_t pix = pix0 + i;
+        if (pix >= hw) break;
+        const int a = (int)(pix / p.Wt), b = (int)(pix % p.Wt);
+        const float *src = p.partial + ((size_t)n * hw + pix) * p.Cout + c;
+        float v = bias;
+        for (int s = 0; s < p.splits; ++s) v += src[(size_t)s * split_stride];
+        p.out[(((size_t)n * p.OHf + (size_t)(a * p.osy + p.ooy)) * p.OWf + (size_t)(b * p.osx + p.oox)) * p.Cs + p.co_off + c] = v;
+        s1 += v; s2 = fmaf(v, v, s2);
     }
     if (p.stats) {
-        const int et = threadIdx.x;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) red[et * 33 + j] = v[j];
-        __syncthreads();
-        {
-            const int j = et & 31, q = et >> 5;
-            float s1 = 0.f, s2 = 0.f;
-            for (int i = 0; i < 32; ++i) {
-                const float x = red[(q * 32 + i) * 33 + j];
-                s1 += x; s2 = fmaf(x, x, s2);
-            }
-            part[(q * 32 + j) * 2] = s1; part[(q * 32 + j) * 2 + 1] = s2;
-        }
-        __syncthreads();
-        if (et < 64) {
-            const int j = et >> 1, w = et & 1, co = c0 + j;
-            if (co < p.Cout) {
-                const double tot = (double)part[j * 2 + w] + (double)part[(32 + j) * 2 + w] + (double)part[(64 + j) * 2 + w] +
-                                   (double)part[(96 + j) * 2 + w];
-                atomicAdd(p.stats + ((size_t)n * p.Cout + co) * 2 + w, tot);
-            }
-        }
+        atomicAdd(p.stats + ((size_t)n * p.Cout + c) * 2, (double)s1);
+        atomicAdd(p.stats + ((size_t)n * p.Cout + c) * 2 + 1, (double)s2);
     }
 }
 
@@ -370,7 +343,7 @@ extern "C" int icon_conv_nhwc(const void *a_hi, const void *a_lo, const int64_t 
     if (rc) return rc;
     if (splits > 1) {
         p.stats = stats;
-        dim3 g2((unsigned)(((int64_t)Ht * Wt + 127) / 128), (unsigned)((Cout + 31) / 32), (unsigned)N);
+        dim3 g2((unsigned)(((int64_t)Ht * Wt + SK_PIX - 1) / SK_PIX), (unsigned)((Cout + 127) / 128), (unsigned)N);
         k_splitk_nhwc<<<g2, 128, 0, stream>>>(p);
         ICON_LAUNCHED();
     }

@@ -175,7 +175,7 @@ class HGFilter(nn.Module):
     def _forward_nhwc(self, x):
         """HGFilters.py:161-197 on the NHWC / TMA / tcgen05 path (icon_b200/nhwc.py), 7x7 stride-2 stem included."""
         from . import nhwc as T
-        with torch.no_grad():
+        with torch.no_grad(), T.stats_arena(x.device):
             r = T.stem_conv7(x, self.conv1, reflect=False)                       # 7x7 s2 on the tensor cores, [N,H/2,W/2,64]
             x = T.norm_relu(r, T.finalize(r, self.bn1))                          # + statistics for conv2.bn1
             x = T.avg_pool2(self.conv2.forward_nhwc(x).dense())
@@ -280,7 +280,7 @@ class GlobalGenerator(nn.Module):
         from . import nhwc as T
         m = self.model
         nd, nb = self.n_downsampling, self.n_blocks
-        with torch.no_grad():
+        with torch.no_grad(), T.stats_arena(x.device):
             raw = T.stem_conv7(x, m[1], reflect=True)
             idx = 4
             for _ in range(nd):
@@ -299,13 +299,11 @@ class GlobalGenerator(nn.Module):
                     idx += 1
             else:
                 op, _ = T.act(raw, T.finalize(raw), relu=True)
-            f32 = None
             for u in range(nd):
                 raw = T.conv_transpose(op, m[idx])
-                last = u == nd - 1
-                op, f32 = T.act(raw, T.finalize(raw), relu=True, operand=not last, f32=last)
+                op, _ = T.act(raw, T.finalize(raw), relu=True)
                 idx += 3
-            return T.conv7_head(f32, m[idx + 1], tanh=(len(m) > idx + 2))
+            return T.conv7_head(op, m[idx + 1], tanh=(len(m) > idx + 2))
 
 
 class NormalNet(nn.Module):

@@ -47,7 +47,43 @@ def _pad64(c):
     return (c + 63) // 64 * 64
 
 
+class _Arena:
+    """One zero-filled fp64 buffer per encoder forward; the per-layer statistics are slices of it (one memset instead
+    of one fill kernel per layer)."""
+    cur = None
+
+    def __init__(self, device, doubles=1 << 18):
+        self.buf = torch.zeros(doubles, dtype=torch.float64, device=device)
+        self.off = 0
+
+    def take(self, n):
+        n = (n + 1) // 2 * 2
+        if self.off + n > self.buf.numel():
+            return None
+        v = self.buf[self.off:self.off + n]
+        self.off += n
+        return v
+
+
+class stats_arena:
+    """with stats_arena(device): ... -- new_stats() inside the block carves from one pre-zeroed buffer."""
+
+    def __init__(self, device):
+        self.device = device
+
+    def __enter__(self):
+        self.prev, _Arena.cur = _Arena.cur, _Arena(self.device)
+
+    def __exit__(self, *exc):
+        _Arena.cur = self.prev
+
+
 def new_stats(N, C, device):
+    a = _Arena.cur
+    if a is not None and a.buf.device == torch.device(device):
+        v = a.take(N * C * 2)
+        if v is not None:
+            return v[:N * C * 2].view(N, C, 2)
     return torch.zeros(N, C, 2, dtype=torch.float64, device=device)
 
 
@@ -71,19 +107,34 @@ def to_nchw(raw):
 
 
 # ------------------------------------------------------------------------------------------------ normalisation
+class NormSpec:
+    """A pending normalisation of `raw`: the producer's sums + the norm layer.  `act` folds it into its own pass when
+    a group has 1, 2, 4 or 8 channels (every norm of the two encoders); `table()` materialises [N, C, 2] scale / shift."""
+
+    def __init__(self, raw, norm):
+        if raw.stats is None:
+            raise _C.IconError("finalize: the producer of this activation accumulated no statistics")
+        self.raw, self.norm = raw, norm
+        self.groups = 0 if norm is None else norm.num_groups
+        self.eps = 1e-5 if norm is None else float(norm.eps)
+        self.gamma = None if norm is None else norm.weight.detach().float().contiguous()
+        self.beta = None if norm is None else norm.bias.detach().float().contiguous()
+
+    def foldable(self):
+        cg = 1 if self.groups == 0 else self.raw.C // self.groups
+        return cg in (1, 2, 4, 8)
+
+    def table(self):
+        raw = self.raw
+        ss = torch.empty(raw.N, raw.C, 2, dtype=torch.float32, device=raw.t.device)
+        check(lib.icon_norm_finalize(_p(raw.stats), _p(self.gamma), _p(self.beta), _p(ss), raw.N, raw.C, self.groups,
+                                     float(raw.H * raw.W), self.eps, _stream()), "icon_norm_finalize")
+        return ss
+
+
 def finalize(raw, norm=None):
-    """Statistics of `raw` -> [N, C, 2] (scale, shift): nn.GroupNorm `norm` (affine) or InstanceNorm2d(affine=False)."""
-    if raw.stats is None:
-        raise _C.IconError("finalize: the producer of this activation accumulated no statistics")
-    ss = torch.empty(raw.N, raw.C, 2, dtype=torch.float32, device=raw.t.device)
-    if norm is None:
-        check(lib.icon_norm_finalize(_p(raw.stats), None, None, _p(ss), raw.N, raw.C, 0, float(raw.H * raw.W), 1e-5,
-                                     _stream()), "icon_norm_finalize")
-    else:
-        check(lib.icon_norm_finalize(_p(raw.stats), _p(norm.weight.detach().float().contiguous()),
-                                     _p(norm.bias.detach().float().contiguous()), _p(ss), raw.N, raw.C, norm.num_groups,
-                                     float(raw.H * raw.W), float(norm.eps), _stream()), "icon_norm_finalize")
-    return ss
+    """Statistics of `raw` + nn.GroupNorm `norm` (affine) or None = InstanceNorm2d(affine=False) -> NormSpec."""
+    return NormSpec(raw, norm)
 
 
 def act(raw, ss=None, relu=False, res=None, operand=True, halo=0, s2d=False, f32=False):
@@ -103,8 +154,20 @@ def act(raw, ss=None, relu=False, res=None, operand=True, halo=0, s2d=False, f32
         out = torch.empty(N, H, W, C, dtype=torch.float32, device=dev)
     if res is not None and tuple(res.shape) != (N, H, W, C):
         raise _C.IconError("act: residual shape mismatch")
-    check(lib.icon_act_nhwc(_p(raw.t), raw.Cs, raw.c_off, _p(ss), _p(res), _p(hi), _p(lo), _p(out), N, H, W, C, Cp,
-                            int(halo), 1 if s2d else 0, 1 if relu else 0, _stream()), "icon_act_nhwc")
+    table = stats = gamma = beta = None
+    groups, eps = 0, 1e-5
+    if isinstance(ss, NormSpec):
+        if ss.raw is not raw:
+            raise _C.IconError("act: the NormSpec belongs to another activation")
+        if ss.foldable():
+            stats, gamma, beta, groups, eps = raw.stats, ss.gamma, ss.beta, ss.groups, ss.eps
+        else:
+            table = ss.table()
+    else:
+        table = ss
+    check(lib.icon_act_nhwc(_p(raw.t), raw.Cs, raw.c_off, _p(table), _p(stats), _p(gamma), _p(beta), groups, eps, _p(res),
+                            _p(hi), _p(lo), _p(out), N, H, W, C, Cp, int(halo), 1 if s2d else 0, 1 if relu else 0,
+                            _stream()), "icon_act_nhwc")
     op = Operand(hi, lo, N, H, W, C, Cp, halo, s2d) if operand else None
     return op, out
 
@@ -358,10 +421,41 @@ def bicubic_up2_add(low, up, stats=True):
 def norm_relu(raw, ss, stats=True):
     """relu(x * scale + shift) as fp32 NHWC WITH the statistics of the result: a normalisation whose output is read
     by another normalisation (HGFilter: relu(bn1(conv1(x))) feeds conv2.bn1, HGFilters.py:162-164)."""
-    return _ew(3, raw.dense(), ss, None, raw.N, raw.H, raw.W, raw.C, stats)
+    return _ew(3, raw.dense(), ss.table() if isinstance(ss, NormSpec) else ss, None, raw.N, raw.H, raw.W, raw.C, stats)
 
 
-def conv7_head(x_f32, m, tanh):
+def conv7_head(op, m, tanh):
+    """ReflectionPad2d(3) + Conv2d(64, <= 3, 7) (+ Tanh), Operand -> NCHW fp32 (FBNet.py:258-261), as GEMM + col2im:
+    an N = 3 implicit GEMM would waste a 128 x N tensor-core tile, so the 64-channel activation is multiplied ONCE with
+    the weights of all 49 taps (a 1 x 1 convolution with 49 * Cout output columns, on the tensor cores), and
+    k_col2im7 adds, for every output pixel, the 49 products of its reflected neighbours."""
+    w = m.weight
+    Cout, Cin, KH, KW = w.shape
+    if (KH, KW) != (7, 7) or Cin != op.C or Cout > 3 or op.halo or op.s2d:
+        raise NotImplementedError("conv7_head: 7x7, <= 3 output channels, plain operand")
+    dev = op.hi.device
+    ncol = 49 * Cout
+    n_tile = _n_tile(ncol)
+    key = (w.data_ptr(), w._version, str(w.device), "head", op.Cp, n_tile)
+    cache = m.__dict__.setdefault("_icon_pack", {})
+    blob = cache.get(key)
+    if blob is None:
+        w2 = torch.zeros(ncol, op.Cp, dtype=torch.float32, device=w.device)          # row (ky*7+kx)*Cout + co
+        w2[:, :Cin] = w.detach().float().permute(2, 3, 0, 1).reshape(ncol, Cin)
+        blob = pack_tiles(w2, n_tile)
+        for k in [k for k in cache if k[:3] != key[:3]]:
+            del cache[k]
+        cache[key] = blob
+    Ps = (ncol + 3) // 4 * 4
+    P = torch.empty(op.N, op.H, op.W, Ps, dtype=torch.float32, device=dev)
+    _launch(op, blob, op.Cp // 64, None, P, 0, ncol, op.H, op.W, 1, 1, 0, 0, [(0, 0, 0, 0)], op.Cp // 64, n_tile, None)
+    y = torch.empty(op.N, Cout, op.H, op.W, dtype=torch.float32, device=dev)
+    b = m.bias.detach().float().contiguous() if m.bias is not None else None
+    check(lib.icon_col2im7(_p(P), _p(b), _p(y), op.N, op.H, op.W, Cout, Ps, 2 if tanh else 0, _stream()), "icon_col2im7")
+    return y
+
+
+def conv7_head_fp32(x_f32, m, tanh):
     """ReflectionPad2d(3) + Conv2d(64, <= 3, 7) (+ Tanh) from fp32 NHWC to NCHW (FBNet.py:258-261)."""
     N, H, W, C = x_f32.shape
     w = m.weight.detach().float().contiguous()

@@ -228,7 +228,9 @@ int icon_conv2d_tc(const float *x, const void *wt_packed, const float *bias, con
  *   n * nplanes + plane (out-of-range coordinates read zeros = zero padding).  stats (optional, zeroed by the
  *   caller): [N][Cout][2] doubles receive per-channel sum / sum of squares of the result (bias included).
  * icon_norm_finalize: stats -> [N][C] (scale, shift) for InstanceNorm2d (groups = 0) / GroupNorm(groups) with affine.
- * icon_act_nhwc: y = [relu](x * scale + shift) [+ res]  -> hi / lo operand tensors (halo > 0: reflection halo;
+ * icon_act_nhwc: y = [relu](x * scale + shift) [+ res], scale / shift either from `scale_shift` or folded in from the
+ *   producer's `stats` (+ GroupNorm gamma / beta, groups = 0: instance norm; 1, 2, 4 or 8 channels per group)
+ *   -> hi / lo operand tensors (halo > 0: reflection halo;
  *   s2d = 1: four parity planes for a stride-2 consumer; channels padded to Cp with zeros) and / or fp32 NHWC.
  * icon_ew_nhwc: mode 0 a + b (+ c), 1 avg_pool2(a), 2 b + bicubic_up2(a, align_corners), 3 relu(a * scale + shift) with
  *   b = the [N][C] (scale, shift) table of icon_norm_finalize; optional stats of the result.
@@ -241,8 +243,14 @@ int icon_conv_nhwc(const void *a_hi, const void *a_lo, const int64_t *dims, cons
                    int n_tile, int splits, double *stats, void *ws, size_t ws_bytes, icon_stream_t stream);
 int icon_norm_finalize(const double *stats, const float *gamma, const float *beta, float *scale_shift, int N, int C,
                        int groups, double count, float eps, icon_stream_t stream);
-int icon_act_nhwc(const float *x, int Cs_in, int ci_off, const float *scale_shift, const float *res, void *hi, void *lo,
-                  float *f32, int N, int H, int W, int C, int Cp, int halo, int s2d, int relu, icon_stream_t stream);
+int icon_act_nhwc(const float *x, int Cs_in, int ci_off, const float *scale_shift, const double *stats, const float *gamma,
+                  const float *beta, int groups, float eps, const float *res, void *hi, void *lo, float *f32, int N, int H,
+                  int W, int C, int Cp, int halo, int s2d, int relu, icon_stream_t stream);
+/* icon_col2im7: second half of the 7 x 7 output head computed as GEMM + col2im: P [N][H][W][Ps] holds, per INPUT pixel,
+ * the products with every tap's weights (column (ky * 7 + kx) * Cout + co; the first half is icon_conv_nhwc with the
+ * regrouped 1 x 1 weights); out[n][co][y][x] = act(bias + sum over the 49 reflected neighbours). */
+int icon_col2im7(const float *P, const float *bias, float *y, int N, int H, int W, int Cout, int Ps, int act,
+                 icon_stream_t stream);
 int icon_ew_nhwc(int mode, const float *a, const float *b, const float *c, float *y, double *stats, int N, int H, int W,
                  int C, icon_stream_t stream);
 int icon_nchw_to_nhwc(const float *x, float *y, double *stats, int N, int C, int64_t HW, icon_stream_t stream);

@@ -223,13 +223,21 @@ def test_normalnet_forward_512_matches_reference_module(golden_dir):
     assert sorted(sd.keys()) == list(g["nml_keys"])
     nn_.load_state_dict(S.seeded_like(sd, 24))
     nn_ = nn_.to(dev).eval()
+    dbatch = {k: v.to(dev) for k, v in batch.items()}
     with torch.no_grad():
-        nF, nB = nn_({k: v.to(dev) for k, v in batch.items()})
+        nF, nB = nn_(dbatch)
+        # the generators' own (pre-normalisation) outputs: n / ||n|| turns an error d on n into ~ d / ||n||, and
+        # NormalNet.py:88-89 has no eps, so the 2e-4 bar on the generator output is propagated per pixel
+        rawF = nn_.netF(torch.cat([dbatch[k] for k in nn_.in_nmlF], 1)).cpu()
+        rawB = nn_.netB(torch.cat([dbatch[k] for k in nn_.in_nmlB], 1)).cpu()
     bg = (batch["image"].abs().sum(1, keepdim=True) == 0)
-    for tag, t in (("F", nF.cpu()), ("B", nB.cpu())):
+    for tag, t, raw in (("F", nF.cpu(), rawF), ("B", nB.cpu(), rawB)):
         assert tuple(t.shape) == (1, 3, 512, 512)
         assert (t[bg.expand_as(t)] == 0).all()                               # masked background is exactly 0
-        assert np.abs(t[:, :, 1::4, 2::4].numpy() - g[f"nml{tag}_sub"]).max() <= 2e-4, tag
+        norm = raw.norm(dim=1, keepdim=True)[:, :, 1::4, 2::4].clamp(min=1e-3).numpy()
+        err = np.abs(t[:, :, 1::4, 2::4].numpy() - g[f"nml{tag}_sub"])
+        assert (err <= 2e-4 / norm + 1e-6).all(), (tag, float(err.max()), float(norm.min()))
+        assert np.median(err) <= 2e-5
         assert np.abs(t.double().sum(dim=(0, 2, 3)).numpy() - g[f"nml{tag}_sum"]).max() <= 1.0
         assert np.abs(t.double().abs().sum(dim=(0, 2, 3)).numpy() - g[f"nml{tag}_abs"]).max() <= 1.0
 
