@@ -57,6 +57,12 @@ k_conv_nhwc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ 
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t bar_full[STAGES], bar_empty[STAGES], bar_acc;
     __shared__ uint32_t tmem_slot;
+    // NT <= 128: the hi | lo weight tiles of a chunk are contiguous in shared memory, i.e. ONE K-major operand of 2 NT
+    // rows, so A_hi * [B_hi ; B_lo] is a single N = 2 NT instruction into two accumulators (summed in the epilogue).
+    // Two MMAs per k-step instead of three, and the wide one runs at the full tensor rate (instructions with N <= 128
+    // are bound by fetching the A operand from shared memory, not by the arithmetic).
+    constexpr bool MERGE = NT <= 128;
+    constexpr int TCOLS = MERGE ? 2 * NT : NT;
     constexpr uint32_t A_BYTES = 128 * 128;                   // one half (hi or lo) of the A tile
     constexpr uint32_t B_BYTES = NT * 256;                    // hi | lo
     constexpr uint32_t STAGE = 2 * A_BYTES + B_BYTES;
@@ -82,7 +88,7 @@ k_conv_nhwc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ 
         tma_prefetch_desc(&map_lo);
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&tmem_slot)), "n"(NT) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&tmem_slot)), "n"(TCOLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     fence_before();
@@ -118,10 +124,17 @@ k_conv_nhwc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ 
                 const uint64_t bh = desc_sw128(sb + 2 * A_BYTES), bl = desc_sw128(sb + 2 * A_BYTES + NT * 128);
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {               // 4 x (K = 16): +32 bytes inside the 128-byte row
-                    mma_ss(tmem, ah + 2 * ks, bh + 2 * ks, IDESC, (i | ks) != 0);
-                    mma_ss(tmem, ah + 2 * ks, bl + 2 * ks, IDESC, 1);
-                    mma_ss(tmem, al + 2 * ks, bh + 2 * ks, IDESC, 1);
+                    if constexpr (MERGE) {
+                        constexpr uint32_t IDESC2 = idesc_f16(128, 2 * NT);
+                        mma_ss(tmem, ah + 2 * ks, bh + 2 * ks, IDESC2, (i | ks) != 0);     // [hi*Whi | hi*Wlo]
+                        mma_ss(tmem, al + 2 * ks, bh + 2 * ks, IDESC, 1);                  // lo*Whi -> first accumulator
+                    } else {
+                        mma_ss(tmem, ah + 2 * ks, bh + 2 * ks, IDESC, (i | ks) != 0);
+                        mma_ss(tmem, ah + 2 * ks, bl + 2 * ks, IDESC, 1);
+                        mma_ss(tmem, al + 2 * ks, bh + 2 * ks, IDESC, 1);
+                    }
                 }
+                (void)bl;
                 commit(s32(&bar_empty[s]));
             }
             commit(s32(&bar_acc));
@@ -154,6 +167,12 @@ k_conv_nhwc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ 
             if (n0 + cb >= p.Cout) break;
             uint32_t acc[32];
             tmem_ld32(tl + cb, acc);
+            if constexpr (MERGE) {
+                uint32_t acc2[32];
+                tmem_ld32(tl + NT + cb, acc2);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[j] = __float_as_uint(__uint_as_float(acc[j]) + __uint_as_float(acc2[j]));
+            }
             float v[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
@@ -206,7 +225,7 @@ k_conv_nhwc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ 
     __syncthreads();
     if (warp == 1) {
         fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(NT) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TCOLS) : "memory");
     }
 }
 

@@ -159,7 +159,8 @@ def act(raw, ss=None, relu=False, res=None, operand=True, halo=0, s2d=False, f32
     if isinstance(ss, NormSpec):
         if ss.raw is not raw:
             raise _C.IconError("act: the NormSpec belongs to another activation")
-        if ss.foldable():
+        if ss.foldable() and N * H * W <= 64 * 64:
+            # small activation: the pass is launch-bound, fold the statistics -> scale / shift step into it
             stats, gamma, beta, groups, eps = raw.stats, ss.gamma, ss.beta, ss.groups, ss.eps
         else:
             table = ss.table()

@@ -13,7 +13,7 @@ for r in csv.DictReader(lines):
     name = re.sub(r"\(.*", "", r["Kernel Name"]).replace("icon::", "").replace("void ", "")
     rows.append((name, v))
 skip = float(sys.argv[2]) if len(sys.argv) > 2 else 0.0
-rows = rows[int(len(rows) * skip):]
+rows = rows[int(len(rows) * skip):] if skip < 1 else rows[-int(skip):]
 agg = {}
 for n, v in rows:
     a = agg.setdefault(n, [0, 0.0]); a[0] += 1; a[1] += v

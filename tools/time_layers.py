@@ -58,5 +58,5 @@ with torch.no_grad():
         print(json.dumps({"layer": f"stem {cin}->64 7x7 s{s} @{h}", "conv_ms": ms,
                           "tflops": 2.0 * cin * 49 * 64 * (h // s) ** 2 / ms / 1e9}), flush=True)
     m = nn.Conv2d(64, 3, 7).to(dev)
-    xf = torch.randn(1, 512, 512, 64, device=dev)
-    print(json.dumps({"layer": "head 64->3 7x7 @512", "conv_ms": timed(lambda: T.conv7_head(xf, m, True))}), flush=True)
+    oph, _ = T.act(T.raw_from_nchw(torch.randn(1, 64, 512, 512, device=dev)))
+    print(json.dumps({"layer": "head 64->3 7x7 @512", "conv_ms": timed(lambda: T.conv7_head(oph, m, True))}), flush=True)
