@@ -37,7 +37,8 @@ struct ConvNhwcParams {
     const float *bias;       // [Cout] or null
     float *out;              // fp32 NHWC [N][OHf][OWf][Cs], this conv writes channels [co_off, co_off + Cout)
     float *partial;          // splits > 1: [splits][N][Ht][Wt][Cout]
-    double *stats;           // [N][Cout][2] (sum, sum of squares) or null; splits == 1 only
+    int *tile_counter;       // splits > 1: [n tiles][pixel tiles], zeroed by the host: arrival count per output tile
+    double *stats;           // [N][Cout][2] (sum, sum of squares) or null
     int N, Ht, Wt;           // logical output grid of this launch (per image)
     int BW, BH, tiles_x, tiles_y;
     int OHf, OWf, osy, osx, ooy, oox;     // out (y, x) = (a * osy + ooy, b * osx + oox)
@@ -50,7 +51,7 @@ struct ConvNhwcParams {
 constexpr int CN_THREADS = 192;
 
 template <int NT, int STAGES>
-__global__ void __launch_bounds__(CN_THREADS, 1)
+__global__ void __launch_bounds__(CN_THREADS, NT == 64 ? 2 : 1)
 k_conv_nhwc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
             const __grid_constant__ ConvNhwcParams p) {
     using namespace um;
@@ -150,74 +151,137 @@ k_conv_nhwc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ 
         fence_after();
         float *red = reinterpret_cast<float *>(smem_raw + (base - s32(smem_raw)));       // [128][33] + [4][32][2]
         float *part = red + 128 * 33;
+        int *s_flag = reinterpret_cast<int *>(part + 4 * 32 * 2);
         const int n0 = blockIdx.y * NT;
         const bool fin = p.splits == 1;
-        float *dst;
-        int dstride;
-        if (fin) {
-            dst = p.out + (((size_t)n * p.OHf + (size_t)(a * p.osy + p.ooy)) * p.OWf + (size_t)(b * p.osx + p.oox)) * p.Cs + p.co_off;
-            dstride = p.Cs;
-        } else {
-            dst = p.partial + ((((size_t)blockIdx.z * p.N + n) * p.Ht + a) * p.Wt + b) * p.Cout;
-            dstride = p.Cout;
+        float *const out_px = p.out + (((size_t)n * p.OHf + (size_t)(a * p.osy + p.ooy)) * p.OWf + (size_t)(b * p.osx + p.oox)) * p.Cs + p.co_off;
+        const size_t split_stride = (size_t)p.N * p.Ht * p.Wt * p.Cout;
+        float *const part_px = fin ? nullptr : p.partial + (((size_t)n * p.Ht + a) * p.Wt + b) * p.Cout;   // split 0
+        bool finalize = fin;
+        if (!fin) {
+            // ---- split-K: park this split's partial tile in the workspace; the LAST split to arrive for the tile
+            //      (per-tile counter) reduces all of them in split order (deterministic) and runs the real epilogue.
+            //      No separate reduction kernel, and the partials are read back while still in L2.
+            float *dst = part_px + (size_t)blockIdx.z * split_stride;
+            const bool vec_ok = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+            for (int cb = 0; cb < NT; cb += 32) {
+                if (n0 + cb >= p.Cout) break;
+                uint32_t acc[32];
+                tmem_ld32(tl + cb, acc);
+                if constexpr (MERGE) {
+                    uint32_t acc2[32];
+                    tmem_ld32(tl + NT + cb, acc2);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc[j] = __float_as_uint(__uint_as_float(acc[j]) + __uint_as_float(acc2[j]));
+                }
+                if (pv) {
+                    if (nchunks == 0) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) acc[j] = 0u;
+                    }
+                    if (vec_ok && n0 + cb + 32 <= p.Cout) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<uint4 *>(dst + n0 + cb + j) = make_uint4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (n0 + cb + j < p.Cout) dst[n0 + cb + j] = __uint_as_float(acc[j]);
+                    }
+                }
+            }
+            __threadfence();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (et == 0) {
+                const int old = atomicAdd(p.tile_counter + (size_t)blockIdx.y * gridDim.x + blockIdx.x, 1);
+                *s_flag = (old == p.splits - 1) ? 1 : 0;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            finalize = *s_flag != 0;
+            if (finalize) __threadfence();
         }
-        (void)dstride;
-        const bool vec_ok = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
-        for (int cb = 0; cb < NT; cb += 32) {
-            if (n0 + cb >= p.Cout) break;
-            uint32_t acc[32];
-            tmem_ld32(tl + cb, acc);
-            if constexpr (MERGE) {
-                uint32_t acc2[32];
-                tmem_ld32(tl + NT + cb, acc2);
+        if (finalize) {
+            const bool vec_out = ((reinterpret_cast<uintptr_t>(out_px) & 15) == 0);
+            const bool vec_in = !fin && ((reinterpret_cast<uintptr_t>(part_px) & 15) == 0) && (split_stride % 4 == 0);
+            for (int cb = 0; cb < NT; cb += 32) {
+                if (n0 + cb >= p.Cout) break;
+                float v[32];
+                if (fin) {
+                    uint32_t acc[32];
+                    tmem_ld32(tl + cb, acc);
+                    if constexpr (MERGE) {
+                        uint32_t acc2[32];
+                        tmem_ld32(tl + NT + cb, acc2);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) acc[j] = __float_as_uint(__uint_as_float(acc[j]) + __uint_as_float(acc2[j]));
-            }
-            float v[32];
+                        for (int j = 0; j < 32; ++j) acc[j] = __float_as_uint(__uint_as_float(acc[j]) + __uint_as_float(acc2[j]));
+                    }
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const int co = n0 + cb + j;
-                float x = nchunks > 0 ? __uint_as_float(acc[j]) : 0.f;
-                if (fin && p.bias && co < p.Cout) x += __ldg(p.bias + co);
-                v[j] = (pv && co < p.Cout) ? x : 0.f;
-            }
-            if (pv) {
-                if (vec_ok && n0 + cb + 32 <= p.Cout) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        *reinterpret_cast<float4 *>(dst + n0 + cb + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    for (int j = 0; j < 32; ++j) v[j] = nchunks > 0 ? __uint_as_float(acc[j]) : 0.f;
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (n0 + cb + j < p.Cout) dst[n0 + cb + j] = v[j];
-                }
-            }
-            if (fin && p.stats) {
-                // per-channel sums over the tile's 128 pixels: transpose through shared memory (the pipeline's
-                // stages are idle: every chunk has been consumed before bar_acc completes)
+                    for (int j = 0; j < 32; ++j) v[j] = 0.f;
+                    if (pv) {
+                        for (int sp = 0; sp < p.splits; ++sp) {
+                            const float *src = part_px + (size_t)sp * split_stride + n0 + cb;
+                            if (vec_in && n0 + cb + 32 <= p.Cout) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) red[et * 33 + j] = v[j];
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                {
-                    const int j = et & 31, q = et >> 5;
-                    float s1 = 0.f, s2 = 0.f;
+                                for (int j = 0; j < 32; j += 4) {
+                                    const float4 t4 = __ldcg(reinterpret_cast<const float4 *>(src + j));
+                                    v[j] += t4.x; v[j + 1] += t4.y; v[j + 2] += t4.z; v[j + 3] += t4.w;
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j)
+                                    if (n0 + cb + j < p.Cout) v[j] += __ldcg(src + j);
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int co = n0 + cb + j;
+                    float x = v[j];
+                    if (p.bias && co < p.Cout) x += __ldg(p.bias + co);
+                    v[j] = (pv && co < p.Cout) ? x : 0.f;
+                }
+                if (pv) {
+                    if (vec_out && n0 + cb + 32 <= p.Cout) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<float4 *>(out_px + n0 + cb + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (n0 + cb + j < p.Cout) out_px[n0 + cb + j] = v[j];
+                    }
+                }
+                if (p.stats) {
+                    // per-channel sums over the tile's 128 pixels: transpose through shared memory (the pipeline's
+                    // stages are idle: every chunk has been consumed before bar_acc completes)
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) red[et * 33 + j] = v[j];
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    {
+                        const int j = et & 31, q = et >> 5;
+                        float s1 = 0.f, s2 = 0.f;
 #pragma unroll 8
-                    for (int i = 0; i < 32; ++i) {
-                        const float x = red[(q * 32 + i) * 33 + j];
-                        s1 += x; s2 = fmaf(x, x, s2);
+                        for (int i = 0; i < 32; ++i) {
+                            const float x = red[(q * 32 + i) * 33 + j];
+                            s1 += x; s2 = fmaf(x, x, s2);
+                        }
+                        part[(q * 32 + j) * 2] = s1; part[(q * 32 + j) * 2 + 1] = s2;
                     }
-                    part[(q * 32 + j) * 2] = s1; part[(q * 32 + j) * 2 + 1] = s2;
-                }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                if (et < 64) {
-                    const int j = et >> 1, w = et & 1, co = n0 + cb + j;
-                    if (co < p.Cout) {
-                        const double tot = (double)part[(0 * 32 + j) * 2 + w] + (double)part[(1 * 32 + j) * 2 + w] +
-                                           (double)part[(2 * 32 + j) * 2 + w] + (double)part[(3 * 32 + j) * 2 + w];
-                        atomicAdd(p.stats + ((size_t)n * p.Cout + co) * 2 + w, tot);
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    if (et < 64) {
+                        const int j = et >> 1, w = et & 1, co = n0 + cb + j;
+                        if (co < p.Cout) {
+                            const double tot = (double)part[(0 * 32 + j) * 2 + w] + (double)part[(1 * 32 + j) * 2 + w] +
+                                               (double)part[(2 * 32 + j) * 2 + w] + (double)part[(3 * 32 + j) * 2 + w];
+                            atomicAdd(p.stats + ((size_t)n * p.Cout + co) * 2 + w, tot);
+                        }
                     }
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
             }
         }
     }
@@ -226,34 +290,6 @@ k_conv_nhwc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ 
     if (warp == 1) {
         fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TCOLS) : "memory");
-    }
-}
-
-// out = bias + sum_s partial[s], + per-(image, channel) statistics.  One thread per channel (coalesced across the
-// block), 32 logical pixels per block, fixed summation order (deterministic).  grid (ceil(HW / 32), ceil(Cout / 128), N).
-constexpr int SK_PIX = 32;
-__global__ void __launch_bounds__(128) k_splitk_nhwc(const __grid_constant__ ConvNhwcParams p) {
-    const int c = blockIdx.y * 128 + threadIdx.x;
-    if (c >= p.Cout) return;
-    const int n = blockIdx.z;
-    const int64_t hw = (int64_t)p.Ht * p.Wt;
-    const int64_t pix0 = (int64_t)blockIdx.x * SK_PIX;
-    const float bias = p.bias ? __ldg(p.bias + c) : 0.f;
-    const size_t split_stride = (size_t)p.N * hw * p.Cout;
-    float s1 = 0.f, s2 = 0.f;
-    for (int i = 0; i < SK_PIX; ++i) {
-        const int64_t pix = pix0 + i;
-        if (pix >= hw) break;
-        const int a = (int)(pix / p.Wt), b = (int)(pix % p.Wt);
-        const float *src = p.partial + ((size_t)n * hw + pix) * p.Cout + c;
-        float v = bias;
-        for (int s = 0; s < p.splits; ++s) v += src[(size_t)s * split_stride];
-        p.out[(((size_t)n * p.OHf + (size_t)(a * p.osy + p.ooy)) * p.OWf + (size_t)(b * p.osx + p.oox)) * p.Cs + p.co_off + c] = v;
-        s1 += v; s2 = fmaf(v, v, s2);
-    }
-    if (p.stats) {
-        atomicAdd(p.stats + ((size_t)n * p.Cout + c) * 2, (double)s1);
-        atomicAdd(p.stats + ((size_t)n * p.Cout + c) * 2 + 1, (double)s2);
     }
 }
 
@@ -310,8 +346,12 @@ static int launch_conv_nhwc(const CUtensorMap &mh, const CUtensorMap &ml, const 
 
 using namespace icon;
 
+static size_t counter_bytes(int N, int Ht, int Wt, int Cout) {       // upper bound over the tile shapes (>= 1 x 16 pixels... 64-ch tiles)
+    const size_t pix_tiles = (size_t)N * ((Ht + 7) / 8 + 1) * ((Wt + 15) / 16 + 1) * 16;
+    return align_up(pix_tiles * ((Cout + 63) / 64) * sizeof(int), 256);
+}
 extern "C" size_t icon_conv_nhwc_workspace_bytes(int N, int Ht, int Wt, int Cout, int splits) {
-    return splits > 1 ? (size_t)splits * N * Ht * Wt * Cout * sizeof(float) : 0;
+    return splits > 1 ? counter_bytes(N, Ht, Wt, Cout) + (size_t)splits * N * Ht * Wt * Cout * sizeof(float) : 0;
 }
 
 extern "C" int icon_conv_nhwc(const void *a_hi, const void *a_lo, const int64_t *dims, const int64_t *strides,
@@ -330,7 +370,7 @@ extern "C" int icon_conv_nhwc(const void *a_hi, const void *a_lo, const int64_t 
                    "icon_conv_nhwc: tensor-map strides must be multiples of 16 bytes");
     ICON_CHECK_ARG(co_off >= 0 && co_off + Cout <= Cs, "icon_conv_nhwc: channel slice outside the output tensor");
     ConvNhwcParams p{};
-    p.wt = (const uint8_t *)wt_packed; p.bias = bias; p.out = out; p.stats = splits == 1 ? stats : nullptr;
+    p.wt = (const uint8_t *)wt_packed; p.bias = bias; p.out = out; p.stats = stats;
     p.N = N; p.Ht = Ht; p.Wt = Wt;
     int bw = 1;
     while (bw < Wt && bw < 16) bw <<= 1;                       // 8 x 16 pixel tiles (taps of neighbouring tiles overlap
@@ -349,22 +389,23 @@ extern "C" int icon_conv_nhwc(const void *a_hi, const void *a_lo, const int64_t 
     ICON_CHECK_ARG((Ht - 1) * osy + ooy < OHf && (Wt - 1) * osx + oox < OWf, "icon_conv_nhwc: output mapping outside the tensor");
     const size_t need = icon_conv_nhwc_workspace_bytes(N, Ht, Wt, Cout, splits);
     if (ws_bytes < need || (need && !ws)) { set_error("icon_conv_nhwc: workspace %zu < %zu", ws_bytes, need); return ICON_ENOSPC; }
-    p.partial = splits > 1 ? (float *)ws : nullptr;
+    p.partial = nullptr; p.tile_counter = nullptr;
     CUtensorMap mh, ml;
     int rc = make_map(&mh, a_hi, dims, strides, p.BW, p.BH);
     if (rc) return rc;
     rc = make_map(&ml, a_lo, dims, strides, p.BW, p.BH);
     if (rc) return rc;
     dim3 grid((unsigned)(p.tiles_x * p.tiles_y * N), (unsigned)((Cout + n_tile - 1) / n_tile), (unsigned)splits);
+    if (splits > 1) {
+        const size_t cb = counter_bytes(N, Ht, Wt, Cout);
+        if ((size_t)grid.x * grid.y * sizeof(int) > cb) { set_error("icon_conv_nhwc: tile counter area too small"); return ICON_ENOSPC; }
+        p.tile_counter = (int *)ws;
+        p.partial = (float *)((char *)ws + cb);
+        ICON_CUDA(cudaMemsetAsync(ws, 0, (size_t)grid.x * grid.y * sizeof(int), stream));
+    }
     if (n_tile == 256) rc = launch_conv_nhwc<256, 2>(mh, ml, p, grid, stream);
     else if (n_tile == 128) rc = launch_conv_nhwc<128, 3>(mh, ml, p, grid, stream);
-    else rc = launch_conv_nhwc<64, 4>(mh, ml, p, grid, stream);
+    else rc = launch_conv_nhwc<64, 2>(mh, ml, p, grid, stream);     // 97 KB: two CTAs per SM overlap prologue / epilogue
     if (rc) return rc;
-    if (splits > 1) {
-        p.stats = stats;
-        dim3 g2((unsigned)(((int64_t)Ht * Wt + SK_PIX - 1) / SK_PIX), (unsigned)((Cout + 127) / 128), (unsigned)N);
-        k_splitk_nhwc<<<g2, 128, 0, stream>>>(p);
-        ICON_LAUNCHED();
-    }
     return ICON_OK;
 }
