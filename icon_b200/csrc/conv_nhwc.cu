@@ -141,12 +141,14 @@ k_conv_nhwc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ 
             commit(s32(&bar_acc));
         }
     } else {
-        // ---------------------------------------------------------------- epilogue: one output pixel per thread
+        // ---------------------------------------------------------------- epilogue
+        // TMEM hands every thread one PIXEL (32 channels at a time); global memory wants a warp on one pixel's
+        // CHANNELS (128 contiguous bytes).  Each warp therefore transposes its 32 x 32 block through shared memory
+        // (conflict-free, stride 33) and then walks its 32 pixels with lane = channel: one coalesced 128-byte store
+        // per pixel, and the per-channel sums for the following norm fall out of the same walk.
         const int q4 = warp & 3, r = q4 * 32 + lane;                      // TMEM lane = pixel index inside the tile
         const int et = (warp - 2) * 32 + lane;                            // 0..127 among the epilogue threads
         const uint32_t tl = tmem + ((uint32_t)(q4 * 32) << 16);
-        const int a = y0 + r / p.BW, b = x0 + r % p.BW;
-        const bool pv = a < p.Ht && b < p.Wt;
         mbar_wait(s32(&bar_acc), 0);
         fence_after();
         float *red = reinterpret_cast<float *>(smem_raw + (base - s32(smem_raw)));       // [128][33] + [4][32][2]
@@ -154,59 +156,16 @@ k_conv_nhwc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ 
         int *s_flag = reinterpret_cast<int *>(part + 4 * 32 * 2);
         const int n0 = blockIdx.y * NT;
         const bool fin = p.splits == 1;
-        float *const out_px = p.out + (((size_t)n * p.OHf + (size_t)(a * p.osy + p.ooy)) * p.OWf + (size_t)(b * p.osx + p.oox)) * p.Cs + p.co_off;
+        const int bw_shift = 31 - __clz(p.BW), bw_mask = p.BW - 1;
         const size_t split_stride = (size_t)p.N * p.Ht * p.Wt * p.Cout;
-        float *const part_px = fin ? nullptr : p.partial + (((size_t)n * p.Ht + a) * p.Wt + b) * p.Cout;   // split 0
-        bool finalize = fin;
-        if (!fin) {
-            // ---- split-K: park this split's partial tile in the workspace; the LAST split to arrive for the tile
-            //      (per-tile counter) reduces all of them in split order (deterministic) and runs the real epilogue.
-            //      No separate reduction kernel, and the partials are read back while still in L2.
-            float *dst = part_px + (size_t)blockIdx.z * split_stride;
-            const bool vec_ok = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+
+        // pass: 0 = final from TMEM (no split-K), 1 = park this split's partial, 2 = fix-up (sum the parked splits)
+        auto run = [&](int pass) {
             for (int cb = 0; cb < NT; cb += 32) {
                 if (n0 + cb >= p.Cout) break;
-                uint32_t acc[32];
-                tmem_ld32(tl + cb, acc);
-                if constexpr (MERGE) {
-                    uint32_t acc2[32];
-                    tmem_ld32(tl + NT + cb, acc2);
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) acc[j] = __float_as_uint(__uint_as_float(acc[j]) + __uint_as_float(acc2[j]));
-                }
-                if (pv) {
-                    if (nchunks == 0) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) acc[j] = 0u;
-                    }
-                    if (vec_ok && n0 + cb + 32 <= p.Cout) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4)
-                            *reinterpret_cast<uint4 *>(dst + n0 + cb + j) = make_uint4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (n0 + cb + j < p.Cout) dst[n0 + cb + j] = __uint_as_float(acc[j]);
-                    }
-                }
-            }
-            __threadfence();
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (et == 0) {
-                const int old = atomicAdd(p.tile_counter + (size_t)blockIdx.y * gridDim.x + blockIdx.x, 1);
-                *s_flag = (old == p.splits - 1) ? 1 : 0;
-            }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            finalize = *s_flag != 0;
-            if (finalize) __threadfence();
-        }
-        if (finalize) {
-            const bool vec_out = ((reinterpret_cast<uintptr_t>(out_px) & 15) == 0);
-            const bool vec_in = !fin && ((reinterpret_cast<uintptr_t>(part_px) & 15) == 0) && (split_stride % 4 == 0);
-            for (int cb = 0; cb < NT; cb += 32) {
-                if (n0 + cb >= p.Cout) break;
-                float v[32];
-                if (fin) {
+                const int co = n0 + cb + lane;
+                const bool cv = co < p.Cout;
+                if (pass != 2) {
                     uint32_t acc[32];
                     tmem_ld32(tl + cb, acc);
                     if constexpr (MERGE) {
@@ -216,72 +175,66 @@ k_conv_nhwc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ 
                         for (int j = 0; j < 32; ++j) acc[j] = __float_as_uint(__uint_as_float(acc[j]) + __uint_as_float(acc2[j]));
                     }
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = nchunks > 0 ? __uint_as_float(acc[j]) : 0.f;
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = 0.f;
-                    if (pv) {
-                        for (int sp = 0; sp < p.splits; ++sp) {
-                            const float *src = part_px + (size_t)sp * split_stride + n0 + cb;
-                            if (vec_in && n0 + cb + 32 <= p.Cout) {
-#pragma unroll
-                                for (int j = 0; j < 32; j += 4) {
-                                    const float4 t4 = __ldcg(reinterpret_cast<const float4 *>(src + j));
-                                    v[j] += t4.x; v[j + 1] += t4.y; v[j + 2] += t4.z; v[j + 3] += t4.w;
-                                }
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < 32; ++j)
-                                    if (n0 + cb + j < p.Cout) v[j] += __ldcg(src + j);
-                            }
-                        }
+                    for (int j = 0; j < 32; ++j) red[r * 33 + j] = nchunks > 0 ? __uint_as_float(acc[j]) : 0.f;
+                    __syncwarp();
+                }
+                const float bias = (pass != 1 && p.bias && cv) ? __ldg(p.bias + co) : 0.f;
+                float s1 = 0.f, s2 = 0.f;
+#pragma unroll 4
+                for (int i = 0; i < 32; ++i) {
+                    const int row = q4 * 32 + i;
+                    const int a = y0 + (row >> bw_shift), b = x0 + (row & bw_mask);
+                    const bool ok = cv && a < p.Ht && b < p.Wt;
+                    const size_t lp = ((size_t)n * p.Ht + a) * p.Wt + b;              // logical pixel
+                    float val = 0.f;
+                    if (pass == 1) {
+                        if (ok) p.partial[(size_t)blockIdx.z * split_stride + lp * p.Cout + co] = red[row * 33 + lane];
+                        continue;
+                    }
+                    if (pass == 0) val = red[row * 33 + lane] + bias;
+                    else if (ok) {
+                        val = bias;
+                        const float *src = p.partial + lp * p.Cout + co;
+                        for (int sp = 0; sp < p.splits; ++sp) val += __ldcg(src + (size_t)sp * split_stride);
+                    }
+                    if (ok) {
+                        p.out[(((size_t)n * p.OHf + (size_t)(a * p.osy + p.ooy)) * p.OWf + (size_t)(b * p.osx + p.oox)) * p.Cs + p.co_off + co] = val;
+                        s1 += val; s2 = fmaf(val, val, s2);
                     }
                 }
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int co = n0 + cb + j;
-                    float x = v[j];
-                    if (p.bias && co < p.Cout) x += __ldg(p.bias + co);
-                    v[j] = (pv && co < p.Cout) ? x : 0.f;
-                }
-                if (pv) {
-                    if (vec_out && n0 + cb + 32 <= p.Cout) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4)
-                            *reinterpret_cast<float4 *>(out_px + n0 + cb + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (n0 + cb + j < p.Cout) out_px[n0 + cb + j] = v[j];
-                    }
-                }
-                if (p.stats) {
-                    // per-channel sums over the tile's 128 pixels: transpose through shared memory (the pipeline's
-                    // stages are idle: every chunk has been consumed before bar_acc completes)
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) red[et * 33 + j] = v[j];
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
-                    {
-                        const int j = et & 31, q = et >> 5;
-                        float s1 = 0.f, s2 = 0.f;
-#pragma unroll 8
-                        for (int i = 0; i < 32; ++i) {
-                            const float x = red[(q * 32 + i) * 33 + j];
-                            s1 += x; s2 = fmaf(x, x, s2);
-                        }
-                        part[(q * 32 + j) * 2] = s1; part[(q * 32 + j) * 2 + 1] = s2;
-                    }
+                __syncwarp();
+                if (pass != 1 && p.stats) {
+                    part[(q4 * 32 + lane) * 2] = s1; part[(q4 * 32 + lane) * 2 + 1] = s2;
                     asm volatile("bar.sync 1, 128;" ::: "memory");
                     if (et < 64) {
-                        const int j = et >> 1, w = et & 1, co = n0 + cb + j;
-                        if (co < p.Cout) {
+                        const int j = et >> 1, w = et & 1, c2 = n0 + cb + j;
+                        if (c2 < p.Cout) {
                             const double tot = (double)part[(0 * 32 + j) * 2 + w] + (double)part[(1 * 32 + j) * 2 + w] +
                                                (double)part[(2 * 32 + j) * 2 + w] + (double)part[(3 * 32 + j) * 2 + w];
-                            atomicAdd(p.stats + ((size_t)n * p.Cout + co) * 2 + w, tot);
+                            atomicAdd(p.stats + ((size_t)n * p.Cout + c2) * 2 + w, tot);
                         }
                     }
                     asm volatile("bar.sync 1, 128;" ::: "memory");
                 }
+            }
+        };
+
+        if (fin) {
+            run(0);
+        } else {
+            // split-K: park this split's partial tile; the LAST split to arrive for the tile (per-tile counter) sums all
+            // of them in split order (deterministic) while they are still in L2 and runs the real epilogue.
+            run(1);
+            __threadfence();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (et == 0) {
+                const int old = atomicAdd(p.tile_counter + (size_t)blockIdx.y * gridDim.x + blockIdx.x, 1);
+                *s_flag = (old == p.splits - 1) ? 1 : 0;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (*s_flag != 0) {
+                __threadfence();
+                run(2);
             }
         }
     }
