@@ -37,7 +37,6 @@ struct ConvNhwcParams {
     const float *bias;       // [Cout] or null
     float *out;              // fp32 NHWC [N][OHf][OWf][Cs], this conv writes channels [co_off, co_off + Cout)
     float *partial;          // splits > 1: [splits][N][Ht][Wt][Cout]
-    int *tile_counter;       // splits > 1: [n tiles][pixel tiles], zeroed by the host: arrival count per output tile
     double *stats;           // [N][Cout][2] (sum, sum of squares) or null
     int N, Ht, Wt;           // logical output grid of this launch (per image)
     int BW, BH, tiles_x, tiles_y;
@@ -153,89 +152,82 @@ k_conv_nhwc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ 
         fence_after();
         float *red = reinterpret_cast<float *>(smem_raw + (base - s32(smem_raw)));       // [128][33] + [4][32][2]
         float *part = red + 128 * 33;
-        int *s_flag = reinterpret_cast<int *>(part + 4 * 32 * 2);
         const int n0 = blockIdx.y * NT;
         const bool fin = p.splits == 1;
         const int bw_shift = 31 - __clz(p.BW), bw_mask = p.BW - 1;
         const size_t split_stride = (size_t)p.N * p.Ht * p.Wt * p.Cout;
 
-        // pass: 0 = final from TMEM (no split-K), 1 = park this split's partial, 2 = fix-up (sum the parked splits)
-        auto run = [&](int pass) {
-            for (int cb = 0; cb < NT; cb += 32) {
-                if (n0 + cb >= p.Cout) break;
-                const int co = n0 + cb + lane;
-                const bool cv = co < p.Cout;
-                if (pass != 2) {
-                    uint32_t acc[32];
-                    tmem_ld32(tl + cb, acc);
-                    if constexpr (MERGE) {
-                        uint32_t acc2[32];
-                        tmem_ld32(tl + NT + cb, acc2);
+        // (a) final tile + statistics: transposed walk (coalesced stores, sums from the same walk)
+        // (b) final tile, no statistics / (c) split-K partial: straight 128-bit stores of the thread's own pixel
+        const int a_me = y0 + (r >> bw_shift), b_me = x0 + (r & bw_mask);
+        const bool pv = a_me < p.Ht && b_me < p.Wt;
+        float *direct = nullptr;
+        if (fin) direct = p.out + (((size_t)n * p.OHf + (size_t)(a_me * p.osy + p.ooy)) * p.OWf + (size_t)(b_me * p.osx + p.oox)) * p.Cs + p.co_off;
+        else direct = p.partial + (size_t)blockIdx.z * split_stride + (((size_t)n * p.Ht + a_me) * p.Wt + b_me) * p.Cout;
+        const bool walk = fin && p.stats != nullptr;
+        const bool vec_ok = ((reinterpret_cast<uintptr_t>(direct) & 15) == 0);
+        for (int cb = 0; cb < NT; cb += 32) {
+            if (n0 + cb >= p.Cout) break;
+            uint32_t acc[32];
+            tmem_ld32(tl + cb, acc);
+            if constexpr (MERGE) {
+                uint32_t acc2[32];
+                tmem_ld32(tl + NT + cb, acc2);
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) acc[j] = __float_as_uint(__uint_as_float(acc[j]) + __uint_as_float(acc2[j]));
-                    }
+                for (int j = 0; j < 32; ++j) acc[j] = __float_as_uint(__uint_as_float(acc[j]) + __uint_as_float(acc2[j]));
+            }
+            if (nchunks == 0) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) red[r * 33 + j] = nchunks > 0 ? __uint_as_float(acc[j]) : 0.f;
-                    __syncwarp();
+                for (int j = 0; j < 32; ++j) acc[j] = 0u;
+            }
+            if (!walk) {
+                if (fin && p.bias) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (n0 + cb + j < p.Cout) acc[j] = __float_as_uint(__uint_as_float(acc[j]) + __ldg(p.bias + n0 + cb + j));
                 }
-                const float bias = (pass != 1 && p.bias && cv) ? __ldg(p.bias + co) : 0.f;
-                float s1 = 0.f, s2 = 0.f;
+                if (pv) {
+                    if (vec_ok && n0 + cb + 32 <= p.Cout) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<uint4 *>(direct + n0 + cb + j) = make_uint4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (n0 + cb + j < p.Cout) direct[n0 + cb + j] = __uint_as_float(acc[j]);
+                    }
+                }
+                continue;
+            }
+            const int co = n0 + cb + lane;
+            const bool cv = co < p.Cout;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) red[r * 33 + j] = __uint_as_float(acc[j]);
+            __syncwarp();
+            const float bias = (p.bias && cv) ? __ldg(p.bias + co) : 0.f;
+            float s1 = 0.f, s2 = 0.f;
 #pragma unroll 4
-                for (int i = 0; i < 32; ++i) {
-                    const int row = q4 * 32 + i;
-                    const int a = y0 + (row >> bw_shift), b = x0 + (row & bw_mask);
-                    const bool ok = cv && a < p.Ht && b < p.Wt;
-                    const size_t lp = ((size_t)n * p.Ht + a) * p.Wt + b;              // logical pixel
-                    float val = 0.f;
-                    if (pass == 1) {
-                        if (ok) p.partial[(size_t)blockIdx.z * split_stride + lp * p.Cout + co] = red[row * 33 + lane];
-                        continue;
-                    }
-                    if (pass == 0) val = red[row * 33 + lane] + bias;
-                    else if (ok) {
-                        val = bias;
-                        const float *src = p.partial + lp * p.Cout + co;
-                        for (int sp = 0; sp < p.splits; ++sp) val += __ldcg(src + (size_t)sp * split_stride);
-                    }
-                    if (ok) {
-                        p.out[(((size_t)n * p.OHf + (size_t)(a * p.osy + p.ooy)) * p.OWf + (size_t)(b * p.osx + p.oox)) * p.Cs + p.co_off + co] = val;
-                        s1 += val; s2 = fmaf(val, val, s2);
-                    }
-                }
-                __syncwarp();
-                if (pass != 1 && p.stats) {
-                    part[(q4 * 32 + lane) * 2] = s1; part[(q4 * 32 + lane) * 2 + 1] = s2;
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
-                    if (et < 64) {
-                        const int j = et >> 1, w = et & 1, c2 = n0 + cb + j;
-                        if (c2 < p.Cout) {
-                            const double tot = (double)part[(0 * 32 + j) * 2 + w] + (double)part[(1 * 32 + j) * 2 + w] +
-                                               (double)part[(2 * 32 + j) * 2 + w] + (double)part[(3 * 32 + j) * 2 + w];
-                            atomicAdd(p.stats + ((size_t)n * p.Cout + c2) * 2 + w, tot);
-                        }
-                    }
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
+            for (int i = 0; i < 32; ++i) {
+                const int row = q4 * 32 + i;
+                const int a = y0 + (row >> bw_shift), b = x0 + (row & bw_mask);
+                if (cv && a < p.Ht && b < p.Wt) {
+                    const float val = red[row * 33 + lane] + bias;
+                    p.out[(((size_t)n * p.OHf + (size_t)(a * p.osy + p.ooy)) * p.OWf + (size_t)(b * p.osx + p.oox)) * p.Cs + p.co_off + co] = val;
+                    s1 += val; s2 = fmaf(val, val, s2);
                 }
             }
-        };
-
-        if (fin) {
-            run(0);
-        } else {
-            // split-K: park this split's partial tile; the LAST split to arrive for the tile (per-tile counter) sums all
-            // of them in split order (deterministic) while they are still in L2 and runs the real epilogue.
-            run(1);
-            __threadfence();
+            __syncwarp();
+            part[(q4 * 32 + lane) * 2] = s1; part[(q4 * 32 + lane) * 2 + 1] = s2;
             asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (et == 0) {
-                const int old = atomicAdd(p.tile_counter + (size_t)blockIdx.y * gridDim.x + blockIdx.x, 1);
-                *s_flag = (old == p.splits - 1) ? 1 : 0;
+            if (et < 64) {
+                const int j = et >> 1, w = et & 1, c2 = n0 + cb + j;
+                if (c2 < p.Cout) {
+                    const double tot = (double)part[(0 * 32 + j) * 2 + w] + (double)part[(1 * 32 + j) * 2 + w] +
+                                       (double)part[(2 * 32 + j) * 2 + w] + (double)part[(3 * 32 + j) * 2 + w];
+                    atomicAdd(p.stats + ((size_t)n * p.Cout + c2) * 2 + w, tot);
+                }
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (*s_flag != 0) {
-                __threadfence();
-                run(2);
-            }
         }
     }
     fence_before();
@@ -243,6 +235,48 @@ k_conv_nhwc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ 
     if (warp == 1) {
         fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TCOLS) : "memory");
+    }
+}
+
+// split-K finish: out = bias + sum_s partial[s] in split order (deterministic) + per-(image, channel) statistics.
+// Block = 32 pixels x 128 channels, 256 threads: lane = channel quad (128-bit loads, coalesced), warp = pixel slot,
+// 4 pixels per thread, every load of a thread independent.  grid (ceil(HW / 32), ceil(Cout / 128), N).
+__global__ void __launch_bounds__(256) k_splitk_nhwc(const __grid_constant__ ConvNhwcParams p) {
+    __shared__ float4 sred[2][8][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int c = blockIdx.y * 128 + lane * 4;
+    const int n = blockIdx.z;
+    const int64_t hw = (int64_t)p.Ht * p.Wt;
+    const size_t split_stride = (size_t)p.N * hw * p.Cout;
+    const bool cv = c < p.Cout;                                 // Cout % 4 == 0 is checked by the host for this kernel
+    float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (cv && p.bias) bias = *reinterpret_cast<const float4 *>(p.bias + c);
+    float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int64_t pix = (int64_t)blockIdx.x * 32 + k * 8 + w;
+        if (!cv || pix >= hw) continue;
+        const float *src = p.partial + ((size_t)n * hw + pix) * p.Cout + c;
+        float4 v = bias;
+        for (int s = 0; s < p.splits; ++s) {
+            const float4 t = __ldcg(reinterpret_cast<const float4 *>(src + (size_t)s * split_stride));
+            v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+        }
+        const int a = (int)(pix / p.Wt), b = (int)(pix % p.Wt);
+        *reinterpret_cast<float4 *>(p.out + (((size_t)n * p.OHf + (size_t)(a * p.osy + p.ooy)) * p.OWf + (size_t)(b * p.osx + p.oox)) * p.Cs +
+                                    p.co_off + c) = v;
+        s1.x += v.x; s1.y += v.y; s1.z += v.z; s1.w += v.w;
+        s2.x = fmaf(v.x, v.x, s2.x); s2.y = fmaf(v.y, v.y, s2.y); s2.z = fmaf(v.z, v.z, s2.z); s2.w = fmaf(v.w, v.w, s2.w);
+    }
+    if (!p.stats) return;
+    sred[0][w][lane] = s1; sred[1][w][lane] = s2;
+    __syncthreads();
+    const int t = threadIdx.x;                                  // 256 threads = 2 x 128 channels
+    const int which = t >> 7, cc = t & 127, co = blockIdx.y * 128 + cc;
+    if (co < p.Cout) {
+        double tot = 0.0;
+        for (int k = 0; k < 8; ++k) tot += (double)reinterpret_cast<const float *>(&sred[which][k][cc >> 2])[cc & 3];
+        atomicAdd(p.stats + ((size_t)n * p.Cout + co) * 2 + which, tot);
     }
 }
 
@@ -299,12 +333,8 @@ static int launch_conv_nhwc(const CUtensorMap &mh, const CUtensorMap &ml, const 
 
 using namespace icon;
 
-static size_t counter_bytes(int N, int Ht, int Wt, int Cout) {       // upper bound over the tile shapes (>= 1 x 16 pixels... 64-ch tiles)
-    const size_t pix_tiles = (size_t)N * ((Ht + 7) / 8 + 1) * ((Wt + 15) / 16 + 1) * 16;
-    return align_up(pix_tiles * ((Cout + 63) / 64) * sizeof(int), 256);
-}
 extern "C" size_t icon_conv_nhwc_workspace_bytes(int N, int Ht, int Wt, int Cout, int splits) {
-    return splits > 1 ? counter_bytes(N, Ht, Wt, Cout) + (size_t)splits * N * Ht * Wt * Cout * sizeof(float) : 0;
+    return splits > 1 ? (size_t)splits * N * Ht * Wt * Cout * sizeof(float) : 0;
 }
 
 extern "C" int icon_conv_nhwc(const void *a_hi, const void *a_lo, const int64_t *dims, const int64_t *strides,
@@ -323,7 +353,7 @@ extern "C" int icon_conv_nhwc(const void *a_hi, const void *a_lo, const int64_t 
                    "icon_conv_nhwc: tensor-map strides must be multiples of 16 bytes");
     ICON_CHECK_ARG(co_off >= 0 && co_off + Cout <= Cs, "icon_conv_nhwc: channel slice outside the output tensor");
     ConvNhwcParams p{};
-    p.wt = (const uint8_t *)wt_packed; p.bias = bias; p.out = out; p.stats = stats;
+    p.wt = (const uint8_t *)wt_packed; p.bias = bias; p.out = out; p.stats = splits == 1 ? stats : nullptr;
     p.N = N; p.Ht = Ht; p.Wt = Wt;
     int bw = 1;
     while (bw < Wt && bw < 16) bw <<= 1;                       // 8 x 16 pixel tiles (taps of neighbouring tiles overlap
@@ -342,23 +372,25 @@ extern "C" int icon_conv_nhwc(const void *a_hi, const void *a_lo, const int64_t 
     ICON_CHECK_ARG((Ht - 1) * osy + ooy < OHf && (Wt - 1) * osx + oox < OWf, "icon_conv_nhwc: output mapping outside the tensor");
     const size_t need = icon_conv_nhwc_workspace_bytes(N, Ht, Wt, Cout, splits);
     if (ws_bytes < need || (need && !ws)) { set_error("icon_conv_nhwc: workspace %zu < %zu", ws_bytes, need); return ICON_ENOSPC; }
-    p.partial = nullptr; p.tile_counter = nullptr;
+    p.partial = splits > 1 ? (float *)ws : nullptr;
+    ICON_CHECK_ARG(splits == 1 || (Cout % 4 == 0 && Cs % 4 == 0 && co_off % 4 == 0 && ((uintptr_t)out & 15) == 0 &&
+                                   (!bias || ((uintptr_t)bias & 15) == 0)),
+                   "icon_conv_nhwc: split-K needs channel counts / offsets that are multiples of 4");
     CUtensorMap mh, ml;
     int rc = make_map(&mh, a_hi, dims, strides, p.BW, p.BH);
     if (rc) return rc;
     rc = make_map(&ml, a_lo, dims, strides, p.BW, p.BH);
     if (rc) return rc;
     dim3 grid((unsigned)(p.tiles_x * p.tiles_y * N), (unsigned)((Cout + n_tile - 1) / n_tile), (unsigned)splits);
-    if (splits > 1) {
-        const size_t cb = counter_bytes(N, Ht, Wt, Cout);
-        if ((size_t)grid.x * grid.y * sizeof(int) > cb) { set_error("icon_conv_nhwc: tile counter area too small"); return ICON_ENOSPC; }
-        p.tile_counter = (int *)ws;
-        p.partial = (float *)((char *)ws + cb);
-        ICON_CUDA(cudaMemsetAsync(ws, 0, (size_t)grid.x * grid.y * sizeof(int), stream));
-    }
     if (n_tile == 256) rc = launch_conv_nhwc<256, 2>(mh, ml, p, grid, stream);
     else if (n_tile == 128) rc = launch_conv_nhwc<128, 3>(mh, ml, p, grid, stream);
     else rc = launch_conv_nhwc<64, 2>(mh, ml, p, grid, stream);     // 97 KB: two CTAs per SM overlap prologue / epilogue
     if (rc) return rc;
+    if (splits > 1) {
+        p.stats = stats;
+        dim3 g2((unsigned)(((int64_t)Ht * Wt + 31) / 32), (unsigned)((Cout + 127) / 128), (unsigned)N);
+        k_splitk_nhwc<<<g2, 256, 0, stream>>>(p);
+        ICON_LAUNCHED();
+    }
     return ICON_OK;
 }

@@ -259,6 +259,8 @@ def _launch(op, blob, wt_chunks, bias, out, co_off, Cout, Ht, Wt, osy, osx, ooy,
     bh = 128 // bw
     n_pix_tiles = N * ((Wt + bw - 1) // bw) * ((Ht + bh - 1) // bh)
     splits = _splits(n_pix_tiles, (Cout + n_tile - 1) // n_tile, len(taps) * cpt)
+    if Cout % 4 or out.shape[3] % 4 or co_off % 4:              # the split-K finish kernel moves 128-bit channel quads
+        splits = 1
     nbytes = lib.icon_conv_nhwc_workspace_bytes(N, Ht, Wt, Cout, splits)
     ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
     OHf, OWf, Cs = out.shape[1], out.shape[2], out.shape[3]
