@@ -287,6 +287,68 @@ def timed(fn, reps, flush=None):
     return ts[len(ts) // 2]
 
 
+def timed_graph(fn, n=8, reps=5):
+    """ms per call of fn() with `n` back-to-back calls captured into one CUDA graph (kernels shorter than the host's
+    launch latency cannot be timed call by call: the events would measure the CPU)."""
+    import torch
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(n):
+            fn()
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); g.replay(); e1.record(); e1.synchronize()
+        ts.append(e0.elapsed_time(e1) / n)
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def encoder_rooflines(dev, peaks, netG):
+    """Tensor-bound kernels of the encoders: the ResnetBlock convolution (80 % of NormalNet's FLOPs) and the whole
+    forwards, algorithmic FLOPs / time against the measured bf16 burst peak (the kernels execute 3 fp16 MMAs per
+    algorithmic one)."""
+    import torch
+    import torch.nn as nn
+    from icon_b200 import nhwc as T, synthetic as S
+    out = []
+    with torch.no_grad():
+        m = nn.Conv2d(1024, 1024, 3, padding=0).to(dev)
+        raw = T.raw_from_nchw(torch.randn(1, 1024, 32, 32, device=dev))
+        op, _ = T.act(raw, halo=1)
+        ms = timed_graph(lambda: T.conv(op, m))
+        flop = 2.0 * 1024 * 9 * 1024 * 32 * 32
+        out.append({"kernel": "k_conv_nhwc<256,2> + k_splitk_nhwc: ResnetBlock conv 1024->1024 3x3 reflect @32x32 (TMA + tcgen05, "
+                              "fp16 hi/lo x3, split-K 4)", "bound": "tensor", "ms": ms, "achieved": flop / ms / 1e9,
+                    "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": flop / ms / 1e9 / peaks["bf16_tflops"],
+                    "executed_frac": 3 * flop / ms / 1e9 / peaks["bf16_tflops"],
+                    "note": "operand traffic L2 -> SM is 96 KB per 64-channel chunk = 59 B/clk/SM at the MMA rate, above the "
+                            "~43 B/clk/SM the L2 sustains chip-wide (B300_MICROARCH.md: ~6300 B/clk): L2-bound, not MMA-bound"})
+        batch = {k: v.to(dev) for k, v in S.encoder_inputs_512(seed=5).items()}
+        for _ in range(3):
+            netG.normal_filter(batch)
+        ms = timed(lambda: netG.normal_filter(batch), 5)
+        out.append({"kernel": "NormalNet.forward 512x512 (2 GlobalGenerators, CUDA-graph replay, all kernels)", "bound": "tensor",
+                    "ms": ms, "achieved": 880.0 / ms, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                    "frac": 880.0 / ms / peaks["bf16_tflops"], "executed_frac": 3 * 880.0 / ms / peaks["bf16_tflops"],
+                    "flop": 880e9})
+        if hasattr(netG, "F_filter"):
+            cin = netG.F_filter.conv1.in_channels
+            xin = torch.cat([batch["image"], batch["T_normal_F"], batch["T_normal_B"]], 1)[:, :cin].contiguous()
+            for _ in range(3):
+                netG.F_filter(xin)
+            ms = timed(lambda: netG.F_filter(xin), 5)
+            gf = 108.3 if cin == 3 else 110.8
+            out.append({"kernel": f"HGFilter.forward 512x512 ({cin} input channels, CUDA-graph replay, all kernels)",
+                        "bound": "tensor", "ms": ms, "achieved": gf / ms, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                        "frac": gf / ms / peaks["bf16_tflops"], "executed_frac": 3 * gf / ms / peaks["bf16_tflops"],
+                        "flop": gf * 1e9})
+    return out
+
+
 def secondary_rooflines(dev, peaks, flush):
     """HBM-bound kernels of the path at their real sizes: algorithmic bytes / CUDA-event time / measured HBM peak."""
     import torch
@@ -574,7 +636,7 @@ def main():
         if rank == 0:
             flush = torch.empty(64 << 20, dtype=torch.float32, device=dev)      # 256 MB > L2
             flush.zero_()
-            extras["rooflines"] = secondary_rooflines(dev, peaks, flush)
+            extras["rooflines"] = secondary_rooflines(dev, peaks, flush) + encoder_rooflines(dev, peaks, netG)
             extras["reference_gpu"] = reference_gpu_encoders(dev, netG)
             del flush
 

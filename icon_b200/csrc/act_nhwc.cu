@@ -63,13 +63,13 @@ struct ActParams {
 
 // one thread = one (destination pixel, 8-channel group)
 __global__ void k_act_nhwc(const __grid_constant__ ActParams p) {
-    const int groups = p.Cp / 8;
-    const int Hd = p.s2d ? p.H : p.H + 2 * p.P, Wd = p.s2d ? p.W : p.W + 2 * p.P;
-    const int64_t total = (int64_t)p.N * Hd * Wd * groups;
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned groups = (unsigned)p.Cp / 8u;                // total < 2^31 is checked by the host: 32-bit index math
+    const unsigned Hd = p.s2d ? p.H : p.H + 2 * p.P, Wd = p.s2d ? p.W : p.W + 2 * p.P;
+    const unsigned total = (unsigned)p.N * Hd * Wd * groups;
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
-    const int g = (int)(i % groups);
-    int64_t r = i / groups;
+    unsigned r = i / groups;
+    const int g = (int)(i - r * groups);
     const int dx = (int)(r % Wd); r /= Wd;
     const int dy = (int)(r % Hd);
     const int n = (int)(r / Hd);
@@ -143,7 +143,7 @@ __global__ void k_act_nhwc(const __grid_constant__ ActParams p) {
             const int plane = (dy & 1) * 2 + (dx & 1);
             d = ((((size_t)n * 4 + plane) * (p.H / 2) + (dy >> 1)) * (p.W / 2) + (dx >> 1)) * p.Cp + c0;
         } else {
-            d = (((size_t)n * Hd + dy) * Wd + dx) * p.Cp + c0;
+            d = (((size_t)n * Hd + dy) * Wd + dx) * (size_t)p.Cp + c0;
         }
         __align__(16) __half h[8], l[8];
 #pragma unroll
@@ -176,18 +176,18 @@ __device__ __forceinline__ void cubic_w4(float t, float (&w)[4]) {     // torch 
     x = 2.f - t; w[3] = ((A * x - 5.f * A) * x + 8.f * A) * x - 4.f * A;
 }
 
-constexpr int EW_PIX = 64;           // pixels per block
+constexpr int EW_PIX = 32;           // pixels per block
 // grid (ceil(H*W / EW_PIX), N), 256 threads: thread = (channel quad, pixel row); C % 4 == 0, C / 4 divides 256
 __global__ void __launch_bounds__(256) k_ew_nhwc(const __grid_constant__ EwParams p) {
     __shared__ float sred[2][256 * 4];                         // [sum | sum of squares][row][channel]: rows * C = 1024
     const int quads = p.C / 4, rows = 256 / quads;
     const int q = threadIdx.x % quads, r0 = threadIdx.x / quads;
     const int n = blockIdx.y;
-    const int64_t hw = (int64_t)p.H * p.W;
-    const int64_t pix0 = (int64_t)blockIdx.x * EW_PIX;
+    const unsigned hw = (unsigned)p.H * (unsigned)p.W;
+    const unsigned pix0 = blockIdx.x * EW_PIX;
     float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
     for (int pr = r0; pr < EW_PIX; pr += rows) {
-        const int64_t pix = pix0 + pr;
+        const unsigned pix = pix0 + pr;
         if (pix >= hw) break;
         const size_t o = ((size_t)n * hw + pix) * p.C + q * 4;
         float4 v;
@@ -471,6 +471,7 @@ extern "C" int icon_act_nhwc(const float *x, int Cs_in, int ci_off, const float 
     p.x = x; p.ss = (const float2 *)scale_shift; p.res = res; p.hi = (__half *)hi; p.lo = (__half *)lo; p.f32 = f32;
     p.N = N; p.H = H; p.W = W; p.C = C; p.Cs_in = Cs_in; p.ci_off = ci_off; p.Cp = Cp; p.P = halo; p.s2d = s2d; p.relu = relu;
     const int64_t total = (int64_t)N * (s2d ? H : H + 2 * halo) * (s2d ? W : W + 2 * halo) * (Cp / 8);
+    ICON_CHECK_ARG(total < (int64_t)1 << 31, "icon_act_nhwc: activation too large for 32-bit indexing");
     k_act_nhwc<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(p);
     ICON_LAUNCHED();
     return ICON_OK;
