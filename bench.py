@@ -419,7 +419,9 @@ def recon_stage(dev, cfg, netG, wl, rank, world, reps=3):
             verts, faces = ops.marching_cubes(occ, 0.5)
             t["marching_cubes"] = timed(lambda: ops.marching_cubes(occ, 0.5), reps)
     torch.cuda.synchronize()
-    if world > 1:
+    if world > 1:                                            # NCCL opens its point-to-point channels on first use: not timed
+        D.gather_meshes([(verts[:8].clone(), faces[:8].clone())], [rank], dev)
+        torch.cuda.synchronize()
         dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -510,6 +512,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")          # keep NCCL's version banner off stdout: ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     from icon_b200 import _C, net, synthetic as S, dist as D

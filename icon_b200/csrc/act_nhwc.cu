@@ -21,6 +21,8 @@ namespace icon {
 __global__ void k_norm_finalize(const double *__restrict__ stats, const float *__restrict__ gamma,
                                 const float *__restrict__ beta, float2 *__restrict__ ss, int N, int C, int groups,
                                 double count, float eps) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N * C) return;
     const int n = i / C, c = i % C;
@@ -63,6 +65,8 @@ struct ActParams {
 
 // one thread = one (destination pixel, 8-channel group)
 __global__ void k_act_nhwc(const __grid_constant__ ActParams p) {
+    pdl_launch_dependents();
+    pdl_wait();
     const unsigned groups = (unsigned)p.Cp / 8u;                // total < 2^31 is checked by the host: 32-bit index math
     const unsigned Hd = p.s2d ? p.H : p.H + 2 * p.P, Wd = p.s2d ? p.W : p.W + 2 * p.P;
     const unsigned total = (unsigned)p.N * Hd * Wd * groups;
@@ -179,6 +183,8 @@ __device__ __forceinline__ void cubic_w4(float t, float (&w)[4]) {     // torch 
 constexpr int EW_PIX = 32;           // pixels per block
 // grid (ceil(H*W / EW_PIX), N), 256 threads: thread = (channel quad, pixel row); C % 4 == 0, C / 4 divides 256
 __global__ void __launch_bounds__(256) k_ew_nhwc(const __grid_constant__ EwParams p) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float sred[2][256 * 4];                         // [sum | sum of squares][row][channel]: rows * C = 1024
     const int quads = p.C / 4, rows = 256 / quads;
     const int q = threadIdx.x % quads, r0 = threadIdx.x / quads;
@@ -262,6 +268,8 @@ __global__ void __launch_bounds__(256) k_ew_nhwc(const __grid_constant__ EwParam
 // x [N][C][HW] -> y [N][HW][C] (+ stats).  grid (ceil(HW / 32), N, ceil(C / 256)), 256 threads.
 __global__ void __launch_bounds__(256) k_nchw_to_nhwc(const float *__restrict__ x, float *__restrict__ y,
                                                       double *__restrict__ stats, int C, int64_t HW) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ float tile[];                            // [32][CB + 1]
     const int n = blockIdx.y;
     const int cb0 = blockIdx.z * 256, CB = min(256, C - cb0);
@@ -295,6 +303,8 @@ __global__ void __launch_bounds__(256) k_nchw_to_nhwc(const float *__restrict__ 
 
 // x [N][HW][Cs] channels [c_off, c_off + C) -> y [N][C][HW]
 __global__ void k_nhwc_to_nchw(const float *__restrict__ x, float *__restrict__ y, int N, int C, int Cs, int c_off, int64_t HW) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int64_t)N * C * HW) return;
     const int64_t pix = i % HW;
@@ -312,6 +322,8 @@ __global__ void k_nhwc_to_nchw(const float *__restrict__ x, float *__restrict__ 
 // split into sy parity planes (stride-2 stem: tap row ky reads plane ky % 2 at row offset ky / 2).
 __global__ void k_stem_pack(const float *__restrict__ x, __half *__restrict__ hi, __half *__restrict__ lo, int N, int Cin,
                             int H, int W, int Cp8, int Wp, int Hrows, int sy, int reflect) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int64_t total = (int64_t)N * sy * Hrows * Wp;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
@@ -399,6 +411,8 @@ __global__ void __launch_bounds__(128) k_conv7_head(const float *__restrict__ x,
 // (49 * Cout columns): the 7 x 7 head (FBNet.py:258-261) as GEMM + col2im instead of an N = 3 implicit GEMM.
 __global__ void __launch_bounds__(256) k_col2im7(const float *__restrict__ P, const float *__restrict__ bias,
                                                  float *__restrict__ y, int N, int H, int W, int Cout, int Ps, int act) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int64_t)N * H * W) return;
     const int ox = (int)(i % W), oy = (int)((i / W) % H), n = (int)(i / ((int64_t)W * H));
@@ -432,7 +446,7 @@ extern "C" int icon_col2im7(const float *P, const float *bias, float *y, int N, 
     cudaStream_t stream = (cudaStream_t)stream_;
     ICON_CHECK_ARG(P && y && N > 0 && H > 3 && W > 3 && Cout >= 1 && Cout <= 3 && Ps >= 49 * Cout, "icon_col2im7: bad argument");
     const int64_t total = (int64_t)N * H * W;
-    k_col2im7<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(P, bias, y, N, H, W, Cout, Ps, act);
+    ICON_CUDA(launch_pdl(k_col2im7, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, P, bias, y, N, H, W, Cout, Ps, act));
     ICON_LAUNCHED();
     return ICON_OK;
 }
@@ -443,7 +457,8 @@ extern "C" int icon_norm_finalize(const double *stats, const float *gamma, const
     ICON_CHECK_ARG(stats && scale_shift && N > 0 && C > 0 && count > 0, "icon_norm_finalize: bad argument");
     ICON_CHECK_ARG(groups <= 0 || C % groups == 0, "icon_norm_finalize: C %% groups != 0");
     ICON_CHECK_ARG((gamma == nullptr) == (beta == nullptr), "icon_norm_finalize: gamma and beta go together");
-    k_norm_finalize<<<(N * C + 127) / 128, 128, 0, stream>>>(stats, gamma, beta, (float2 *)scale_shift, N, C, groups, count, eps);
+    ICON_CUDA(launch_pdl(k_norm_finalize, dim3((N * C + 127) / 128), dim3(128), 0, stream, stats, gamma, beta, (float2 *)scale_shift, N,
+                         C, groups, count, eps));
     ICON_LAUNCHED();
     return ICON_OK;
 }
@@ -472,7 +487,7 @@ extern "C" int icon_act_nhwc(const float *x, int Cs_in, int ci_off, const float 
     p.N = N; p.H = H; p.W = W; p.C = C; p.Cs_in = Cs_in; p.ci_off = ci_off; p.Cp = Cp; p.P = halo; p.s2d = s2d; p.relu = relu;
     const int64_t total = (int64_t)N * (s2d ? H : H + 2 * halo) * (s2d ? W : W + 2 * halo) * (Cp / 8);
     ICON_CHECK_ARG(total < (int64_t)1 << 31, "icon_act_nhwc: activation too large for 32-bit indexing");
-    k_act_nhwc<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(p);
+    ICON_CUDA(launch_pdl(k_act_nhwc, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, p));
     ICON_LAUNCHED();
     return ICON_OK;
 }
@@ -488,7 +503,7 @@ extern "C" int icon_ew_nhwc(int mode, const float *a, const float *b, const floa
     p.a = a; p.b = mode == 3 ? nullptr : b; p.c = c; p.y = y; p.stats = stats; p.N = N; p.H = H; p.W = W; p.C = C; p.mode = mode;
     p.ss = mode == 3 ? (const float2 *)b : nullptr;
     dim3 grid((unsigned)(((int64_t)H * W + EW_PIX - 1) / EW_PIX), (unsigned)N);
-    k_ew_nhwc<<<grid, 256, 0, stream>>>(p);
+    ICON_CUDA(launch_pdl(k_ew_nhwc, grid, dim3(256), 0, stream, p));
     ICON_LAUNCHED();
     return ICON_OK;
 }
@@ -497,7 +512,7 @@ extern "C" int icon_nchw_to_nhwc(const float *x, float *y, double *stats, int N,
     cudaStream_t stream = (cudaStream_t)stream_;
     ICON_CHECK_ARG(x && y && N > 0 && C > 0 && HW > 0, "icon_nchw_to_nhwc: bad argument");
     dim3 grid((unsigned)((HW + 31) / 32), (unsigned)N, (unsigned)((C + 255) / 256));
-    k_nchw_to_nhwc<<<grid, 256, 32 * (min(C, 256) + 1) * sizeof(float), stream>>>(x, y, stats, C, HW);
+    ICON_CUDA(launch_pdl(k_nchw_to_nhwc, grid, dim3(256), 32 * (min(C, 256) + 1) * sizeof(float), stream, x, y, stats, C, HW));
     ICON_LAUNCHED();
     return ICON_OK;
 }
@@ -506,7 +521,7 @@ extern "C" int icon_nhwc_to_nchw(const float *x, float *y, int N, int C, int Cs,
     cudaStream_t stream = (cudaStream_t)stream_;
     ICON_CHECK_ARG(x && y && N > 0 && C > 0 && c_off >= 0 && c_off + C <= Cs && HW > 0, "icon_nhwc_to_nchw: bad argument");
     const int64_t total = (int64_t)N * C * HW;
-    k_nhwc_to_nchw<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(x, y, N, C, Cs, c_off, HW);
+    ICON_CUDA(launch_pdl(k_nhwc_to_nchw, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, x, y, N, C, Cs, c_off, HW));
     ICON_LAUNCHED();
     return ICON_OK;
 }
@@ -518,8 +533,8 @@ extern "C" int icon_stem_pack(const float *x, void *hi, void *lo, int N, int Cin
     ICON_CHECK_ARG((Cp8 == 8 || Cp8 == 16) && Cin <= Cp8 && (sy == 1 || sy == 2), "icon_stem_pack: Cin <= 16, stride 1 or 2");
     ICON_CHECK_ARG(Wp >= W + 7 && Hrows * sy >= H + 6, "icon_stem_pack: padded extent too small");
     const int64_t total = (int64_t)N * sy * Hrows * Wp;
-    k_stem_pack<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(x, (__half *)hi, (__half *)lo, N, Cin, H, W, Cp8, Wp, Hrows,
-                                                                    sy, reflect);
+    ICON_CUDA(launch_pdl(k_stem_pack, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, x, (__half *)hi, (__half *)lo, N, Cin,
+                         H, W, Cp8, Wp, Hrows, sy, reflect));
     ICON_LAUNCHED();
     return ICON_OK;
 }

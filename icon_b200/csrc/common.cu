@@ -3,6 +3,8 @@
 #include <stdarg.h>
 #include <atomic>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace icon {
@@ -152,5 +154,16 @@ int device_sm_count() {
         counts[dev] = n;
     }
     return counts[dev];
+}
+}  // namespace icon
+
+namespace icon {
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("ICON_B200_PDL");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
 }
 }  // namespace icon

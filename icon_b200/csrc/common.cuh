@@ -51,6 +51,28 @@ static inline bool device_needs_setup(bool (&flags)[ICON_MAX_DEVICES], int *dev_
 }
 int device_sm_count();    // multiprocessors of the CURRENT device (cached per device)
 
+// Programmatic dependent launch (PDL): the encoders are chains of ~600 short kernels; launched with the programmatic-
+// stream-serialization attribute a kernel's CTAs may be scheduled while its predecessor drains, do their local set-up
+// (barrier init, TMEM allocation, descriptor prefetch) and then block in pdl_wait() until the predecessor has completed
+// and its writes are visible.  Every kernel launched through launch_pdl() calls pdl_launch_dependents() first thing and
+// pdl_wait() before its first global-memory access; both are no-ops for a normal launch.  ICON_B200_PDL=0 disables it.
+bool pdl_enabled();
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                     Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
+
 // carve a workspace
 struct Carver {
     char *base;

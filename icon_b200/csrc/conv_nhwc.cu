@@ -68,6 +68,7 @@ k_conv_nhwc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ 
     constexpr uint32_t STAGE = 2 * A_BYTES + B_BYTES;
     const uint32_t base = (s32(smem_raw) + 1023u) & ~1023u;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    pdl_launch_dependents();
 
     const int nchunks_all = p.ntaps * p.cpt;
     const int per = (nchunks_all + p.splits - 1) / p.splits;
@@ -95,6 +96,7 @@ k_conv_nhwc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ 
     __syncthreads();
     fence_after();
     const uint32_t tmem = tmem_slot;
+    pdl_wait();                       // everything above is local set-up; the predecessor's outputs are read from here on
 
     if (warp == 0) {
         if (lane == 0) {
@@ -243,6 +245,8 @@ k_conv_nhwc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ 
 // 4 pixels per thread, every load of a thread independent.  grid (ceil(HW / 32), ceil(Cout / 128), N).
 __global__ void __launch_bounds__(256) k_splitk_nhwc(const __grid_constant__ ConvNhwcParams p) {
     __shared__ float4 sred[2][8][32];
+    pdl_launch_dependents();
+    pdl_wait();
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int c = blockIdx.y * 128 + lane * 4;
     const int n = blockIdx.z;
@@ -324,7 +328,7 @@ static int launch_conv_nhwc(const CUtensorMap &mh, const CUtensorMap &ml, const 
     static bool attr_set[ICON_MAX_DEVICES] = {};
     if (device_needs_setup(attr_set))
         ICON_CUDA(cudaFuncSetAttribute(k_conv_nhwc<NT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    k_conv_nhwc<NT, STAGES><<<grid, CN_THREADS, smem, stream>>>(mh, ml, p);
+    ICON_CUDA(launch_pdl(k_conv_nhwc<NT, STAGES>, grid, dim3(CN_THREADS), (size_t)smem, stream, mh, ml, p));
     ICON_LAUNCHED();
     return ICON_OK;
 }
@@ -389,7 +393,7 @@ extern "C" int icon_conv_nhwc(const void *a_hi, const void *a_lo, const int64_t 
     if (splits > 1) {
         p.stats = stats;
         dim3 g2((unsigned)(((int64_t)Ht * Wt + 31) / 32), (unsigned)((Cout + 127) / 128), (unsigned)N);
-        k_splitk_nhwc<<<g2, 256, 0, stream>>>(p);
+        ICON_CUDA(launch_pdl(k_splitk_nhwc, g2, dim3(256), 0, stream, p));
         ICON_LAUNCHED();
     }
     return ICON_OK;

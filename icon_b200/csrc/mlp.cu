@@ -400,16 +400,22 @@ extern "C" int icon_query(int prior, const float *points, int64_t stride_c, int6
         profile_mark(4, stream);
         return rc;
     }
+    profile_mark(0, stream);                         // stage timers: [0,1) point transform, [1,3) empty, [3,4) gather + MLP
     int rc = run_points_only(points, stride_c, stride_n, N, h_calib, w.xyz4, stream);
     if (rc) return rc;
+    profile_mark(1, stream); profile_mark(2, stream); profile_mark(3, stream);
     q.xyz4 = w.xyz4;
     if (prior == ICON_PRIOR_PIFU) {
         ICON_CHECK_ARG(C + 1 == c0, "icon_query: pifu prior expects c0 = C + 1 (C=%d c0=%d)", C, c0);
-        return launch_any<1>(q, mlp_tc, stream);
+        rc = launch_any<1>(q, mlp_tc, stream);
+        profile_mark(4, stream);
+        return rc;
     }
     if (prior == ICON_PRIOR_PAMIR) {
         ICON_CHECK_ARG(vol_feat && VD >= 2 && C + 7 == c0, "icon_query: pamir prior expects vol_feat and c0 = C + 7");
-        return launch_any<2>(q, mlp_tc, stream);
+        rc = launch_any<2>(q, mlp_tc, stream);
+        profile_mark(4, stream);
+        return rc;
     }
     set_error("icon_query: unknown prior %d", prior);
     return ICON_EINVAL;
