@@ -162,7 +162,7 @@ bool pdl_enabled() {
     static int v = -1;
     if (v < 0) {
         const char *e = getenv("ICON_B200_PDL");
-        v = (e && e[0] == '0') ? 0 : 1;
+        v = (e && e[0] == '1') ? 1 : 0;          // measured on B200: slower than plain graph replay here (profiles/r2_summary.md)
     }
     return v == 1;
 }

@@ -55,7 +55,8 @@ int device_sm_count();    // multiprocessors of the CURRENT device (cached per d
 // stream-serialization attribute a kernel's CTAs may be scheduled while its predecessor drains, do their local set-up
 // (barrier init, TMEM allocation, descriptor prefetch) and then block in pdl_wait() until the predecessor has completed
 // and its writes are visible.  Every kernel launched through launch_pdl() calls pdl_launch_dependents() first thing and
-// pdl_wait() before its first global-memory access; both are no-ops for a normal launch.  ICON_B200_PDL=0 disables it.
+// pdl_wait() before its first global-memory access; both are no-ops for a normal launch.  OFF by default (it measured
+// slower than plain CUDA-graph replay: dependents park on the SMs the predecessor's tail still needs); ICON_B200_PDL=1 enables it.
 bool pdl_enabled();
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

@@ -308,7 +308,14 @@ static int g_mlp_impl = 1;
 
 template <int MODE>
 static int launch_any(const QueryParams &q, const void *tc, cudaStream_t stream) {
-    if (g_mlp_impl == 1 && tc) return launch_mlp_tc(MODE, q, tc, stream);
+    if (g_mlp_impl == 1) {
+        if (!tc) {          // never degrade silently to the 10x slower FP32 kernel: the caller asked for tcgen05
+            set_error("icon_query / icon_mlp_only: the tcgen05 MLP needs the packed tensor-core weight blob (mlp_tc == NULL); "
+                      "pass it or select the FP32 kernel with icon_set_mlp_impl(0)");
+            return ICON_EINVAL;
+        }
+        return launch_mlp_tc(MODE, q, tc, stream);
+    }
     return launch_mlp<MODE>(q, stream);
 }
 

@@ -5,12 +5,15 @@
 //   kaolin check_sign              -> +x ray parity
 //   barycentric_coordinates_of_projection + the four gathers -> cmap / normal / vis
 //
-// Design (DESIGN.md "SDF"): one thread per query point.
-//   nearest face  depth-first walk of the implicit 4-ary AABB tree over Morton-sorted faces
-//                 (icon_smpl_prepare), children visited near-to-far, a subtree is skipped only
-//                 when its box is strictly farther than the current best (with float slack), a
-//                 face only when its bounding sphere is; ties resolve to the lowest ORIGINAL
-//                 face index, exactly like the brute-force scan.
+// Design: one WARP per group of PPW query points (32 Morton-adjacent lattice points on the dense grid).
+//   nearest face  (A) greedy descent of the implicit 4-ary AABB tree over Morton-sorted faces (icon_smpl_prepare) to
+//                 the leaf nearest the warp centre: a first bound for every lane; (B) breadth-first cull of the
+//                 tree, 32 child boxes per step, ballot-compacted into a 16-bit frontier in shared memory, against
+//                 the warp's bound; (C) the surviving leaves' faces are culled 32 at a time by bounding sphere, and
+//                 every lane tests the survivors against ITS OWN best through two cheap lower bounds (sphere,
+//                 support function) before the exact Ericson distance.  A subtree / face is skipped only when its
+//                 bound is strictly farther than the current best (float slack on every bound); ties resolve to
+//                 the lowest ORIGINAL face index, exactly like the brute-force scan.
 //   sign          the faces listed in the point's yz cell (256 x 256 grid over the mesh's yz
 //                 box) are the only ones a +x ray can hit; each is tested with the same
 //                 Moller-Trumbore code as the brute-force scan, so the hit COUNT is identical.

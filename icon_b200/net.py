@@ -104,7 +104,8 @@ class MLP(nn.Module):
         if self.training:
             raise NotImplementedError("fused MLP kernel is inference-only (BatchNorm1d in eval mode)")
         sd = self.state_dict()
-        key = _tensor_key(*[sd[k] for k in sorted(sd)])
+        own = list(self.parameters()) + list(self.buffers())      # the module's own tensors: alive as long as the cache is
+        key = tuple((id(t), t._version, t.data_ptr(), str(t.device)) for t in own)
         if self._packed is None or key != self._packed_key:
             dev = self.filters[0].weight.device
             self._packed = ops.pack_mlp(sd, self.c0, device=dev)
