@@ -160,6 +160,118 @@ __global__ void k_act_nhwc(const __grid_constant__ ActParams p) {
     }
 }
 
+// ---------------------------------------------------------------------------------------- split-K finish + InstanceNorm + act
+// The ResnetBlock layers (FBNet.py:268-319: conv -> InstanceNorm2d(affine=False) [-> ReLU] [+ x]) run split-K, and an
+// instance norm only needs the statistics of ONE channel over the image: a block that owns 8 channels of all H x W
+// pixels can sum the parked split-K partials (fixed order), keep the result in shared memory, compute mean / variance
+// locally (two-pass, no atomics: deterministic), normalise, and write the next convolution's hi / lo operand (with its
+// reflection halo) + the fp32 copy the residual connection needs -- split-K finish, norm statistics, finalize and the
+// act pass in one kernel, the un-normalised tensor never goes to HBM.   grid (C / 8, N), 256 threads, H*W*32 B smem.
+struct SkActParams {
+    const float *partial;    // [splits][N][H][W][C]
+    const float *bias;       // [C] or null
+    const float *res;        // fp32 NHWC [N][H][W][C] or null: added after norm (+ ReLU)
+    __half *hi, *lo;         // [N][H + 2P][W + 2P][Cp]
+    float *f32;              // [N][H][W][C] or null
+    int splits, N, H, W, C, Cp, P, relu;
+    float eps;
+};
+
+__global__ void __launch_bounds__(256) k_splitk_in_act(const __grid_constant__ SkActParams p) {
+    extern __shared__ float4 sval[];                           // [H*W][2]: 8 channels per pixel
+    __shared__ float sw[8][8];
+    __shared__ float s_mean[8], s_rstd[8];
+    pdl_launch_dependents();
+    pdl_wait();
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int c0 = blockIdx.x * 8, n = blockIdx.y;
+    const int HW = p.H * p.W;
+    const size_t split_stride = (size_t)p.N * HW * p.C;
+    float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+    if (p.bias) { b0 = *reinterpret_cast<const float4 *>(p.bias + c0); b1 = *reinterpret_cast<const float4 *>(p.bias + c0 + 4); }
+    float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int pix = tid; pix < HW; pix += 256) {
+        const float *src = p.partial + ((size_t)n * HW + pix) * p.C + c0;
+        float4 v0 = b0, v1 = b1;
+        for (int k = 0; k < p.splits; ++k) {
+            const float4 t0 = __ldcg(reinterpret_cast<const float4 *>(src + (size_t)k * split_stride));
+            const float4 t1 = __ldcg(reinterpret_cast<const float4 *>(src + (size_t)k * split_stride + 4));
+            v0.x += t0.x; v0.y += t0.y; v0.z += t0.z; v0.w += t0.w;
+            v1.x += t1.x; v1.y += t1.y; v1.z += t1.z; v1.w += t1.w;
+        }
+        sval[2 * pix] = v0; sval[2 * pix + 1] = v1;
+        s[0] += v0.x; s[1] += v0.y; s[2] += v0.z; s[3] += v0.w; s[4] += v1.x; s[5] += v1.y; s[6] += v1.z; s[7] += v1.w;
+    }
+    auto block_sum8 = [&](float (&x)[8], float *out8) {        // deterministic: shuffle tree, then warps in order
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+#pragma unroll
+            for (int o = 16; o; o >>= 1) x[k] += __shfl_xor_sync(0xffffffffu, x[k], o);
+        __syncthreads();
+        if (lane == 0)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) sw[w][k] = x[k];
+        __syncthreads();
+        if (tid < 8) {
+            double t = 0.0;
+            for (int ww = 0; ww < 8; ++ww) t += (double)sw[ww][tid];
+            out8[tid] = (float)(t / (double)HW);
+        }
+        __syncthreads();
+    };
+    block_sum8(s, s_mean);
+    float q[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int pix = tid; pix < HW; pix += 256) {                 // centred second moment from shared memory
+        const float4 v0 = sval[2 * pix], v1 = sval[2 * pix + 1];
+        float d;
+        d = v0.x - s_mean[0]; q[0] = fmaf(d, d, q[0]); d = v0.y - s_mean[1]; q[1] = fmaf(d, d, q[1]);
+        d = v0.z - s_mean[2]; q[2] = fmaf(d, d, q[2]); d = v0.w - s_mean[3]; q[3] = fmaf(d, d, q[3]);
+        d = v1.x - s_mean[4]; q[4] = fmaf(d, d, q[4]); d = v1.y - s_mean[5]; q[5] = fmaf(d, d, q[5]);
+        d = v1.z - s_mean[6]; q[6] = fmaf(d, d, q[6]); d = v1.w - s_mean[7]; q[7] = fmaf(d, d, q[7]);
+    }
+    block_sum8(q, s_rstd);                                      // holds the (biased) variance for the moment
+    if (tid < 8) s_rstd[tid] = rsqrtf(s_rstd[tid] + p.eps);
+    __syncthreads();
+    const int Hd = p.H + 2 * p.P, Wd = p.W + 2 * p.P;
+    for (int d = tid; d < Hd * Wd; d += 256) {
+        const int dy = d / Wd, dx = d - dy * Wd;
+        int sy = dy - p.P, sx = dx - p.P;
+        const bool interior = sy >= 0 && sy < p.H && sx >= 0 && sx < p.W;
+        sy = sy < 0 ? -sy : (sy >= p.H ? 2 * p.H - 2 - sy : sy);
+        sx = sx < 0 ? -sx : (sx >= p.W ? 2 * p.W - 2 - sx : sx);
+        const int pix = sy * p.W + sx;
+        const float4 v0 = sval[2 * pix], v1 = sval[2 * pix + 1];
+        float y[8] = {(v0.x - s_mean[0]) * s_rstd[0], (v0.y - s_mean[1]) * s_rstd[1], (v0.z - s_mean[2]) * s_rstd[2],
+                      (v0.w - s_mean[3]) * s_rstd[3], (v1.x - s_mean[4]) * s_rstd[4], (v1.y - s_mean[5]) * s_rstd[5],
+                      (v1.z - s_mean[6]) * s_rstd[6], (v1.w - s_mean[7]) * s_rstd[7]};
+        if (p.relu) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) y[k] = fmaxf(y[k], 0.f);
+        }
+        if (p.res) {
+            const float *rs = p.res + ((size_t)n * HW + pix) * p.C + c0;
+            const float4 r0 = *reinterpret_cast<const float4 *>(rs), r1 = *reinterpret_cast<const float4 *>(rs + 4);
+            y[0] += r0.x; y[1] += r0.y; y[2] += r0.z; y[3] += r0.w; y[4] += r1.x; y[5] += r1.y; y[6] += r1.z; y[7] += r1.w;
+        }
+        if (p.f32 && interior) {
+            float *fd = p.f32 + ((size_t)n * HW + pix) * p.C + c0;
+            *reinterpret_cast<float4 *>(fd) = make_float4(y[0], y[1], y[2], y[3]);
+            *reinterpret_cast<float4 *>(fd + 4) = make_float4(y[4], y[5], y[6], y[7]);
+        }
+        if (p.hi) {
+            __align__(16) __half h[8], l[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                h[k] = __float2half_rn(y[k]);
+                l[k] = __float2half_rn(y[k] - __half2float(h[k]));
+            }
+            const size_t o = (((size_t)n * Hd + dy) * Wd + dx) * (size_t)p.Cp + c0;
+            *reinterpret_cast<uint4 *>(p.hi + o) = *reinterpret_cast<const uint4 *>(h);
+            *reinterpret_cast<uint4 *>(p.lo + o) = *reinterpret_cast<const uint4 *>(l);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------- elementwise + statistics
 struct EwParams {
     const float *a, *b, *c;  // fp32 NHWC
@@ -488,6 +600,28 @@ extern "C" int icon_act_nhwc(const float *x, int Cs_in, int ci_off, const float 
     const int64_t total = (int64_t)N * (s2d ? H : H + 2 * halo) * (s2d ? W : W + 2 * halo) * (Cp / 8);
     ICON_CHECK_ARG(total < (int64_t)1 << 31, "icon_act_nhwc: activation too large for 32-bit indexing");
     ICON_CUDA(launch_pdl(k_act_nhwc, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, p));
+    ICON_LAUNCHED();
+    return ICON_OK;
+}
+
+extern "C" int icon_splitk_instnorm_act(const float *partial, int splits, const float *bias, const float *res, void *hi, void *lo,
+                                        float *f32, int N, int H, int W, int C, int Cp, int halo, int relu, float eps,
+                                        icon_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    ICON_CHECK_ARG(partial && splits >= 1 && N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && Cp >= C && Cp % 8 == 0,
+                   "icon_splitk_instnorm_act: bad argument (C %% 8 == 0)");
+    ICON_CHECK_ARG((hi == nullptr) == (lo == nullptr) && (hi || f32), "icon_splitk_instnorm_act: hi and lo go together; need an output");
+    ICON_CHECK_ARG(halo >= 0 && halo < H && halo < W, "icon_splitk_instnorm_act: reflection halo %d needs halo < H, W", halo);
+    ICON_CHECK_ARG(Cp == C || !hi, "icon_splitk_instnorm_act: channel padding is not written here (C must be a multiple of 64)");
+    const size_t smem = (size_t)H * W * 32;
+    ICON_CHECK_ARG(smem <= 200 * 1024, "icon_splitk_instnorm_act: image of %d x %d pixels does not fit shared memory", H, W);
+    static bool attr_set[ICON_MAX_DEVICES] = {};
+    if (device_needs_setup(attr_set))
+        ICON_CUDA(cudaFuncSetAttribute(k_splitk_in_act, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    SkActParams p{};
+    p.partial = partial; p.bias = bias; p.res = res; p.hi = (__half *)hi; p.lo = (__half *)lo; p.f32 = f32;
+    p.splits = splits; p.N = N; p.H = H; p.W = W; p.C = C; p.Cp = Cp; p.P = halo; p.relu = relu; p.eps = eps;
+    ICON_CUDA(launch_pdl(k_splitk_in_act, dim3((unsigned)(C / 8), (unsigned)N), dim3(256), smem, stream, p));
     ICON_LAUNCHED();
     return ICON_OK;
 }

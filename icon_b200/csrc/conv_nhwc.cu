@@ -347,7 +347,8 @@ extern "C" int icon_conv_nhwc(const void *a_hi, const void *a_lo, const int64_t 
                               int ntaps, const int *taps /* ntaps x (dy, dx, plane, wtap) */, int cpt, int n_tile, int splits,
                               double *stats, void *ws, size_t ws_bytes, icon_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    ICON_CHECK_ARG(a_hi && a_lo && dims && strides && wt_packed && out && taps, "icon_conv_nhwc: null pointer");
+    ICON_CHECK_ARG(a_hi && a_lo && dims && strides && wt_packed && taps, "icon_conv_nhwc: null pointer");
+    ICON_CHECK_ARG(out || splits > 1, "icon_conv_nhwc: out == NULL (park the split-K partials only) needs splits > 1");
     ICON_CHECK_ARG(N > 0 && Ht > 0 && Wt > 0 && Cout > 0 && cpt > 0 && nplanes > 0, "icon_conv_nhwc: bad size");
     ICON_CHECK_ARG(ntaps >= 1 && ntaps <= MAX_TAPS, "icon_conv_nhwc: 1..%d taps", MAX_TAPS);
     ICON_CHECK_ARG(n_tile == 64 || n_tile == 128 || n_tile == 256, "icon_conv_nhwc: n_tile must be 64, 128 or 256");
@@ -373,12 +374,12 @@ extern "C" int icon_conv_nhwc(const void *a_hi, const void *a_lo, const int64_t 
         ICON_CHECK_ARG(taps[4 * i + 2] >= 0 && taps[4 * i + 2] < nplanes && (taps[4 * i + 3] + 1) * cpt <= wt_chunks,
                        "icon_conv_nhwc: tap %d out of range", i);
     }
-    ICON_CHECK_ARG((Ht - 1) * osy + ooy < OHf && (Wt - 1) * osx + oox < OWf, "icon_conv_nhwc: output mapping outside the tensor");
+    ICON_CHECK_ARG(!out || ((Ht - 1) * osy + ooy < OHf && (Wt - 1) * osx + oox < OWf), "icon_conv_nhwc: output mapping outside the tensor");
     const size_t need = icon_conv_nhwc_workspace_bytes(N, Ht, Wt, Cout, splits);
     if (ws_bytes < need || (need && !ws)) { set_error("icon_conv_nhwc: workspace %zu < %zu", ws_bytes, need); return ICON_ENOSPC; }
     p.partial = splits > 1 ? (float *)ws : nullptr;
-    ICON_CHECK_ARG(splits == 1 || (Cout % 4 == 0 && Cs % 4 == 0 && co_off % 4 == 0 && ((uintptr_t)out & 15) == 0 &&
-                                   (!bias || ((uintptr_t)bias & 15) == 0)),
+    ICON_CHECK_ARG(splits == 1 || !out || (Cout % 4 == 0 && Cs % 4 == 0 && co_off % 4 == 0 && ((uintptr_t)out & 15) == 0 &&
+                                           (!bias || ((uintptr_t)bias & 15) == 0)),
                    "icon_conv_nhwc: split-K needs channel counts / offsets that are multiples of 4");
     CUtensorMap mh, ml;
     int rc = make_map(&mh, a_hi, dims, strides, p.BW, p.BH);
@@ -390,7 +391,7 @@ extern "C" int icon_conv_nhwc(const void *a_hi, const void *a_lo, const int64_t 
     else if (n_tile == 128) rc = launch_conv_nhwc<128, 3>(mh, ml, p, grid, stream);
     else rc = launch_conv_nhwc<64, 2>(mh, ml, p, grid, stream);     // 97 KB: two CTAs per SM overlap prologue / epilogue
     if (rc) return rc;
-    if (splits > 1) {
+    if (splits > 1 && out) {
         p.stats = stats;
         dim3 g2((unsigned)(((int64_t)Ht * Wt + 31) / 32), (unsigned)((Cout + 127) / 128), (unsigned)N);
         ICON_CUDA(launch_pdl(k_splitk_nhwc, g2, dim3(256), 0, stream, p));

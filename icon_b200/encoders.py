@@ -283,22 +283,26 @@ class GlobalGenerator(nn.Module):
         with torch.no_grad(), T.stats_arena(x.device):
             raw = T.stem_conv7(x, m[1], reflect=True)
             idx = 4
-            for _ in range(nd):
-                op, _ = T.act(raw, T.finalize(raw), relu=True, s2d=True)
-                raw = T.conv(op, m[idx])
+            op = None
+            for d in range(nd):
+                if op is None:
+                    op, _ = T.act(raw, T.finalize(raw), relu=True, s2d=True)
+                last = d == nd - 1
+                if last and nb > 0:
+                    # conv -> IN -> ReLU, and the result is both the first ResnetBlock's operand and its residual
+                    op, cur = T.conv_instnorm_act(op, m[idx], relu=True, halo=1, f32=True)
+                elif last:
+                    op, cur = T.conv_instnorm_act(op, m[idx], relu=True)
+                else:
+                    raw = T.conv(op, m[idx])
+                    op = None
                 idx += 3
-            if nb > 0:
-                op, cur = T.act(raw, T.finalize(raw), relu=True, halo=1, f32=True)
-                for b in range(nb):
-                    blk = m[idx].conv_block
-                    r1 = T.conv(op, blk[1])
-                    op1, _ = T.act(r1, T.finalize(r1), relu=True, halo=1)
-                    r2 = T.conv(op1, blk[5])
-                    last = b == nb - 1
-                    op, cur = T.act(r2, T.finalize(r2), res=cur, halo=0 if last else 1, f32=not last)
-                    idx += 1
-            else:
-                op, _ = T.act(raw, T.finalize(raw), relu=True)
+            for b in range(nb):
+                blk = m[idx].conv_block
+                last = b == nb - 1
+                op1, _ = T.conv_instnorm_act(op, blk[1], relu=True, halo=1)
+                op, cur = T.conv_instnorm_act(op1, blk[5], res=cur, halo=0 if last else 1, f32=not last)
+                idx += 1
             for u in range(nd):
                 raw = T.conv_transpose(op, m[idx])
                 op, _ = T.act(raw, T.finalize(raw), relu=True)

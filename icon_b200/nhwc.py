@@ -269,8 +269,8 @@ def _launch(op, blob, wt_chunks, bias, out, co_off, Cout, Ht, Wt, osy, osx, ooy,
                              _p(stats), _p(ws), nbytes, _stream()), "icon_conv_nhwc")
 
 
-def conv(op, m, out=None, co_off=0, stats=True):
-    """nn.Conv2d on an Operand -> Raw (fp32 NHWC, optionally a channel slice of `out`).
+def _conv_taps(op, m):
+    """Tap table of nn.Conv2d `m` on Operand `op` -> (taps, OH, OW, KH * KW).
 
     Zero padding = TMA out-of-bounds fill (operand without halo); reflection padding = operand with halo == padding
     (the ReflectionPad2d in front of the conv); stride 2 = space-to-depth operand."""
@@ -279,7 +279,6 @@ def conv(op, m, out=None, co_off=0, stats=True):
     if Cin != op.C or m.groups != 1 or m.dilation[0] != 1 or m.stride[0] != m.stride[1]:
         raise _C.IconError(f"conv: operand has {op.C} channels, weight {tuple(w.shape)}")
     s, pad = m.stride[0], (op.halo if op.halo else m.padding[0])
-    cpt = op.Cp // 64
     taps = []
     if s == 1:
         if op.s2d:
@@ -301,6 +300,14 @@ def conv(op, m, out=None, co_off=0, stats=True):
         OH, OW = (op.H + 2 * pad - KH) // 2 + 1, (op.W + 2 * pad - KW) // 2 + 1
     else:
         raise NotImplementedError("conv: stride 1 or 2 (all convolutions of the path)")
+    return taps, OH, OW, KH * KW
+
+
+def conv(op, m, out=None, co_off=0, stats=True):
+    """nn.Conv2d on an Operand -> Raw (fp32 NHWC, optionally a channel slice of `out`)."""
+    taps, OH, OW, ntap = _conv_taps(op, m)
+    Cout = m.weight.shape[0]
+    cpt = op.Cp // 64
     n_tile = _n_tile(Cout)
     blob = packed_weight(m, False, op.Cp, n_tile)
     dev = op.hi.device
@@ -308,8 +315,51 @@ def conv(op, m, out=None, co_off=0, stats=True):
         out = torch.empty(op.N, OH, OW, Cout, dtype=torch.float32, device=dev)
     st = new_stats(op.N, Cout, dev) if stats else None
     bias = m.bias.detach().float().contiguous() if m.bias is not None else None
-    _launch(op, blob, KH * KW * cpt, bias, out, co_off, Cout, OH, OW, 1, 1, 0, 0, taps, cpt, n_tile, st)
+    _launch(op, blob, ntap * cpt, bias, out, co_off, Cout, OH, OW, 1, 1, 0, 0, taps, cpt, n_tile, st)
     return Raw(out, C=Cout, c_off=co_off, stats=st)
+
+
+def conv_instnorm_act(op, m, relu=False, res=None, halo=0, f32=False):
+    """nn.Conv2d -> InstanceNorm2d(affine=False) [-> ReLU] [+ res] -> (Operand with reflection halo, fp32 or None).
+
+    When the convolution runs split-K (small images: the ResnetBlocks) and the image fits a block's shared memory,
+    the split-K reduction, the norm statistics and the normalise / split pass are ONE kernel after the MMA kernel
+    (icon_splitk_instnorm_act); otherwise conv + act."""
+    taps, OH, OW, ntap = _conv_taps(op, m)
+    Cout = m.weight.shape[0]
+    cpt = op.Cp // 64
+    n_tile = _n_tile(Cout)
+    dev = op.hi.device
+    N = op.N
+    bw = 1
+    while bw < OW and bw < 16:
+        bw <<= 1
+    bh = 128 // bw
+    n_pix_tiles = N * ((OW + bw - 1) // bw) * ((OH + bh - 1) // bh)
+    splits = _splits(n_pix_tiles, (Cout + n_tile - 1) // n_tile, len(taps) * cpt)
+    if splits == 1 or Cout % 64 or OH * OW * 32 > 200 * 1024:
+        r = conv(op, m)
+        return act(r, finalize(r), relu=relu, res=res, halo=halo, f32=f32)
+    blob = packed_weight(m, False, op.Cp, n_tile)
+    nbytes = lib.icon_conv_nhwc_workspace_bytes(N, OH, OW, Cout, splits)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    NI, Hd, Wd, Cp = op.hi.shape
+    dims = (ctypes.c_int64 * 4)(Cp, Wd, Hd, NI)
+    strides = (ctypes.c_int64 * 3)(Cp, Wd * Cp, Hd * Wd * Cp)
+    flat = [int(v) for t in taps for v in t]
+    tap_arr = (ctypes.c_int * len(flat))(*flat)
+    check(lib.icon_conv_nhwc(_p(op.hi), _p(op.lo), dims, strides, _p(blob), ntap * cpt, None, None, OH, OW, Cout, 0, Cout, N,
+                             OH, OW, 1, 1, 0, 0, 4 if op.s2d else 1, len(taps), tap_arr, cpt, n_tile, splits, None, _p(ws),
+                             nbytes, _stream()), "icon_conv_nhwc(park)")
+    hi = torch.empty(N, OH + 2 * halo, OW + 2 * halo, Cout, dtype=torch.float16, device=dev)
+    lo = torch.empty_like(hi)
+    out = torch.empty(N, OH, OW, Cout, dtype=torch.float32, device=dev) if f32 else None
+    bias = m.bias.detach().float().contiguous() if m.bias is not None else None
+    if res is not None and tuple(res.shape) != (N, OH, OW, Cout):
+        raise _C.IconError("conv_instnorm_act: residual shape mismatch")
+    check(lib.icon_splitk_instnorm_act(_p(ws), splits, _p(bias), _p(res), _p(hi), _p(lo), _p(out), N, OH, OW, Cout, Cout,
+                                       int(halo), 1 if relu else 0, 1e-5, _stream()), "icon_splitk_instnorm_act")
+    return Operand(hi, lo, N, OH, OW, Cout, Cout, halo, False), out
 
 
 def stem_conv7(x, m, reflect, stats=True):

@@ -246,6 +246,14 @@ int icon_norm_finalize(const double *stats, const float *gamma, const float *bet
 int icon_act_nhwc(const float *x, int Cs_in, int ci_off, const float *scale_shift, const double *stats, const float *gamma,
                   const float *beta, int groups, float eps, const float *res, void *hi, void *lo, float *f32, int N, int H,
                   int W, int C, int Cp, int halo, int s2d, int relu, icon_stream_t stream);
+/* icon_splitk_instnorm_act: for a split-K convolution followed by InstanceNorm2d(affine=False) [+ ReLU] [+ residual]
+ * (the ResnetBlocks): call icon_conv_nhwc with out == NULL (the split partials stay parked in its workspace
+ * [splits][N][H][W][C]), then this -- one kernel sums the partials in split order, computes each channel's mean /
+ * variance over the image inside a block (no atomics), normalises and writes the next operand (hi / lo with a
+ * reflection halo) and / or the fp32 tensor. */
+int icon_splitk_instnorm_act(const float *partial, int splits, const float *bias, const float *res, void *hi, void *lo,
+                             float *f32, int N, int H, int W, int C, int Cp, int halo, int relu, float eps,
+                             icon_stream_t stream);
 /* icon_col2im7: second half of the 7 x 7 output head computed as GEMM + col2im: P [N][H][W][Ps] holds, per INPUT pixel,
  * the products with every tap's weights (column (ky * 7 + kx) * Cout + co; the first half is icon_conv_nhwc with the
  * regrouped 1 x 1 weights); out[n][co][y][x] = act(bias + sum over the 49 reflected neighbours). */

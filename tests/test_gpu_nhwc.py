@@ -235,3 +235,29 @@ def test_norm_relu_with_statistics_of_the_result():
     assert (T.to_nchw(r).cpu() - ref).abs().max() <= 3e-5
     assert torch.allclose(r.stats.cpu()[..., 0], ref.double().sum(dim=(2, 3)), rtol=1e-4, atol=1e-2)
     assert torch.allclose(r.stats.cpu()[..., 1], (ref.double() ** 2).sum(dim=(2, 3)), rtol=1e-4, atol=1e-2)
+
+
+@pytest.mark.parametrize("c,hw,relu,use_res", [(1024, 32, True, False), (1024, 32, False, True), (256, 16, True, True),
+                                               (64, 64, True, False)])
+def test_conv_instnorm_act_fused_splitk_path(c, hw, relu, use_res):
+    """ResnetBlock half: ReflectionPad2d(1) + Conv2d(k3) -> InstanceNorm2d [-> ReLU] [+ x] with the split-K reduction,
+    the statistics and the normalise / split pass fused into one kernel (falls back to conv + act when no split-K)."""
+    dev = _cuda()
+    from icon_b200 import nhwc as T
+    conv = nn.Conv2d(c, c, 3, padding=0)
+    x = torch.randn(1, c, hw, hw, generator=_g(c + hw))
+    res = torch.randn(1, c, hw, hw, generator=_g(7))
+    with torch.no_grad():
+        y = F.instance_norm(conv(F.pad(x, (1, 1, 1, 1), mode="reflect")))
+        ref = (F.relu(y) if relu else y) + (res if use_res else 0)
+    op, _ = T.act(T.raw_from_nchw(x.to(dev)), halo=1)
+    resd = res.permute(0, 2, 3, 1).contiguous().to(dev) if use_res else None
+    out_op, f = T.conv_instnorm_act(op, conv.to(dev), relu=relu, res=resd, halo=1, f32=True)
+    got = f.permute(0, 3, 1, 2).cpu()
+    assert (got - ref).abs().max() <= 5e-5 * max(1.0, ref.abs().max().item())
+    val = (out_op.hi.float() + out_op.lo.float()).permute(0, 3, 1, 2).cpu()
+    pad = F.pad(ref, (1, 1, 1, 1), mode="reflect")
+    assert (val - pad).abs().max() <= 6e-5 * max(1.0, ref.abs().max().item())
+    # deterministic: no atomics anywhere on this path
+    out_op2, f2 = T.conv_instnorm_act(op, conv, relu=relu, res=resd, halo=1, f32=True)
+    assert torch.equal(f, f2) and torch.equal(out_op.hi, out_op2.hi) and torch.equal(out_op.lo, out_op2.lo)
