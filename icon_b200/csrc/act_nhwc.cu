@@ -292,7 +292,7 @@ __device__ __forceinline__ void cubic_w4(float t, float (&w)[4]) {     // torch 
     x = 2.f - t; w[3] = ((A * x - 5.f * A) * x + 8.f * A) * x - 4.f * A;
 }
 
-constexpr int EW_PIX = 32;           // pixels per block
+constexpr int EW_PIX = 64;           // pixels per block (more blocks = more same-address fp64 atomics: 32 measured slower)
 // grid (ceil(H*W / EW_PIX), N), 256 threads: thread = (channel quad, pixel row); C % 4 == 0, C / 4 divides 256
 __global__ void __launch_bounds__(256) k_ew_nhwc(const __grid_constant__ EwParams p) {
     pdl_launch_dependents();

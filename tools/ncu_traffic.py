@@ -36,7 +36,7 @@ def read(rep):
     for r in rows[2:]:
         if len(r) < len(hdr):
             continue
-        d = {"kernel": re.sub(r"<.*", "", r[col["Kernel Name"]]).replace("icon::", "").replace("void ", "").strip()}
+        d = {"kernel": re.sub(r"[<(].*", "", r[col["Kernel Name"]]).replace("icon::", "").replace("void ", "").strip()}
         for k, short in WANT.items():
             if k in col:
                 try:
