@@ -20,6 +20,7 @@
 // Results are identical to brute force over all faces (icon_sdf_bruteforce, the CPU oracle):
 // the pruning is conservative and the per-face arithmetic is the same code (geom.cuh).
 #include <float.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "geom.cuh"
@@ -185,7 +186,7 @@ __device__ __forceinline__ float box_far2(V3 p, float4 lo, float4 hi) {   // squ
 template <int PPW>
 __global__ void __launch_bounds__(SW_T) k_sdf_warp(const float4 *__restrict__ xyz4, const int32_t *__restrict__ perm,
                                                    int64_t N, MeshView m, float *__restrict__ rec,
-                                                   int32_t *__restrict__ face) {
+                                                   int32_t *__restrict__ face, int order) {
     constexpr int REP = 32 / PPW;
     constexpr int FR_CAP = fr_cap(PPW);
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -279,6 +280,37 @@ __global__ void __launch_bounds__(SW_T) k_sdf_warp(const float4 *__restrict__ xy
         // some face lies within the nearest far-corner distance of c -> within that + rw of every lane
         const float l2 = sqrtf(warp_min(far2)) + rw;
         if (l2 < ubw2) { ubw2 = l2; ub2 = (ubw2 * 1.00001f + 1e-6f) * (ubw2 * 1.00001f + 1e-6f); }
+        __syncwarp();
+    }
+    // ---- near-first order of the surviving leaves.  The lanes' bounds only tighten while faces are tested, and the
+    //      warp-level cull of a chunk uses the LOOSEST lane bound: leaves that can beat even the tightest current
+    //      bound (box distance <= min over lanes of sqrt(best)) go first, so that the bounds are (nearly) final
+    //      before the long tail of barely-surviving leaves is looked at -- most of the tail then fails the one
+    //      warp-level test instead of 32 per-lane tests.  Order does not affect results (ties: lowest face index).
+    if (order && !overflow && n > 8) {
+        const float ubmin = warp_min(best * rsqrtf(fmaxf(best, 1e-30f))) * 1.00001f + 1e-6f;
+        const float t2 = ubmin * ubmin;
+        int n1 = 0, n2 = 0;
+        for (int base = 0; base < n; base += 32) {
+            const int slot = base + lane;
+            const bool valid = slot < n;
+            int leaf = 0;
+            bool near = false;
+            if (valid) {
+                leaf = (int)S.fr[cur][slot];
+                const float4 lo = __ldg(m.nodes + 2 * (size_t)leaf), hi = __ldg(m.nodes + 2 * (size_t)leaf + 1);
+                const float gx = fmaxf(fmaxf(lo.x - whi.x, wlo.x - hi.x), 0.f);
+                const float gy = fmaxf(fmaxf(lo.y - whi.y, wlo.y - hi.y), 0.f);
+                const float gz = fmaxf(fmaxf(lo.z - whi.z, wlo.z - hi.z), 0.f);
+                near = fmaf(gz, gz, fmaf(gy, gy, gx * gx)) <= t2;
+            }
+            const unsigned mn = __ballot_sync(0xffffffffu, valid && near), mf = __ballot_sync(0xffffffffu, valid && !near);
+            const unsigned lt = (1u << lane) - 1u;
+            if (valid && near) S.fr[cur ^ 1][n1 + __popc(mn & lt)] = (unsigned short)leaf;
+            if (valid && !near) S.fr[cur ^ 1][n - 1 - (n2 + __popc(mf & lt))] = (unsigned short)leaf;
+            n1 += __popc(mn); n2 += __popc(mf);
+        }
+        cur ^= 1;
         __syncwarp();
     }
     STAT(0, 1); STAT(1, overflow ? 1 : 0); STAT(2, n);
@@ -423,6 +455,7 @@ __global__ void __launch_bounds__(256) k_sdf_brute(const float *__restrict__ pts
 
 // points-per-warp policy of k_sdf_warp (see its header comment); icon_set_sdf_policy() overrides it for tuning
 static int64_t g_sdf_ppw32_from = 6000000, g_sdf_ppw8_from = 300000;
+static int g_sdf_order = -1;          // near-first leaf order; ICON_B200_SDF_ORDER=0 disables (A/B measurements)
 static int g_sdf_ppw_force = 0;
 
 // ---------------------------------------------------------------- host-side pipeline pieces
@@ -489,11 +522,15 @@ int run_sdf(const float *points, int64_t sc, int64_t sn, int64_t N, const float 
     // the point count alone cannot tell the two apart -- callers that know can pin it (icon_set_sdf_policy).
     int ppw = N >= g_sdf_ppw32_from ? 32 : (N >= g_sdf_ppw8_from ? 8 : 1);
     if (g_sdf_ppw_force) ppw = g_sdf_ppw_force;
+    if (g_sdf_order < 0) {
+        const char *e = getenv("ICON_B200_SDF_ORDER");
+        g_sdf_order = (e && e[0] == '0') ? 0 : 1;
+    }
     const int wpb = SW_T / 32;
     const int64_t nwarps = (N + ppw - 1) / ppw;
     const unsigned nblk_w = (unsigned)((nwarps + wpb - 1) / wpb);
 #define ICON_SDF_LAUNCH(P) k_sdf_warp<P><<<nblk_w, SW_T, sizeof(WarpSmem<fr_cap(P)>) * (SW_T / 32), stream>>>( \
-        w.xyz4, w.perm, N, m, rec, face)
+        w.xyz4, w.perm, N, m, rec, face, g_sdf_order)
     switch (ppw) {
         case 32: ICON_SDF_LAUNCH(32); break;
         case 16: ICON_SDF_LAUNCH(16); break;
