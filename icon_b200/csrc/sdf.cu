@@ -455,7 +455,8 @@ __global__ void __launch_bounds__(256) k_sdf_brute(const float *__restrict__ pts
 
 // points-per-warp policy of k_sdf_warp (see its header comment); icon_set_sdf_policy() overrides it for tuning
 static int64_t g_sdf_ppw32_from = 6000000, g_sdf_ppw8_from = 300000;
-static int g_sdf_order = -1;          // near-first leaf order; ICON_B200_SDF_ORDER=0 disables (A/B measurements)
+static int g_sdf_order = -1;          // near-first leaf order: measured neutral-to-slower on the dense lattice (8.43 vs 8.33 ms,
+                                      // profiles/r2_summary.md), so OFF unless ICON_B200_SDF_ORDER=1
 static int g_sdf_ppw_force = 0;
 
 // ---------------------------------------------------------------- host-side pipeline pieces
@@ -524,7 +525,7 @@ int run_sdf(const float *points, int64_t sc, int64_t sn, int64_t N, const float 
     if (g_sdf_ppw_force) ppw = g_sdf_ppw_force;
     if (g_sdf_order < 0) {
         const char *e = getenv("ICON_B200_SDF_ORDER");
-        g_sdf_order = (e && e[0] == '0') ? 0 : 1;
+        g_sdf_order = (e && e[0] == '1') ? 1 : 0;
     }
     const int wpb = SW_T / 32;
     const int64_t nwarps = (N + ppw - 1) / ppw;
