@@ -330,8 +330,8 @@ class NormalNet(nn.Module):
         C = _conv_ops()
         inF = torch.cat([in_tensor[name] for name in self.in_nmlF], dim=1)
         inB = torch.cat([in_tensor[name] for name in self.in_nmlB], dim=1)
-        nmlF = self.netF(inF)
-        nmlB = self.netB(inB)
+        from .graphs import run_pair
+        nmlF, nmlB = run_pair(lambda: self.netF(inF), lambda: self.netB(inB))      # two streams: independent chains
         # NormalNet.py:88-97: n / ||n||_2 over C (no eps), times (sum_c |image| != 0)
         return C.normalize_mask(nmlF, in_tensor["image"]), C.normalize_mask(nmlB, in_tensor["image"])
 

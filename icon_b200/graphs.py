@@ -18,6 +18,53 @@ _ENABLED = os.environ.get("ICON_B200_CUDA_GRAPHS", "1") != "0"
 MAX_GRAPHS_PER_MODULE = 4
 
 
+_CONCURRENT = os.environ.get("ICON_B200_CONCURRENT", "1") != "0"
+_SIDE = {}
+_SLOT = [0]           # which of the two concurrent chains is being enqueued: a module called on both (HGFilter on the front
+                      # and the back map) needs one captured graph (= one set of static buffers) per chain
+
+
+def concurrent(flag=None):
+    """Run independent encoder forwards of one call (NormalNet's two generators, HGFilter on the front / back normal
+    maps) on two CUDA streams.  Each is a chain of several hundred short kernels, most of them smaller than the GPU:
+    side by side they fill SMs the other leaves idle.  Environment ICON_B200_CONCURRENT=0 disables."""
+    global _CONCURRENT
+    if flag is not None:
+        _CONCURRENT = bool(flag)
+    return _CONCURRENT
+
+
+def run_pair(fn_a, fn_b):
+    """(fn_a(), fn_b()) -- fn_b on a side stream when concurrency is on and the tensors live on a GPU.  The results
+    are safe to use on the current stream afterwards (the side stream is joined, its outputs are marked as used
+    by the current stream for the caching allocator)."""
+    if not (_CONCURRENT and torch.cuda.is_available()) or torch.cuda.is_current_stream_capturing():
+        return fn_a(), fn_b()
+    main = torch.cuda.current_stream()
+    key = main.device_index
+    side = _SIDE.get(key)
+    if side is None:
+        side = _SIDE[key] = torch.cuda.Stream(device=key)
+    side.wait_stream(main)
+    _SLOT[0] = 1
+    try:
+        with torch.cuda.stream(side):
+            b = fn_b()
+    finally:
+        _SLOT[0] = 0
+    a = fn_a()
+    main.wait_stream(side)
+
+    def mark(t):
+        if isinstance(t, torch.Tensor) and t.is_cuda:
+            t.record_stream(main)
+        elif isinstance(t, (list, tuple)):
+            for u in t:
+                mark(u)
+    mark(b)
+    return a, b
+
+
 def enable(flag=True):
     """Process-wide switch (also: environment ICON_B200_CUDA_GRAPHS=0)."""
     global _ENABLED
@@ -45,7 +92,7 @@ class GraphedForward:
     def _key(self, x, extra):
         m = self.module
         weights = tuple((t.data_ptr(), t._version) for t in list(m.parameters()) + list(m.buffers()))
-        return (tuple(x.shape), x.dtype, str(x.device), extra, weights)
+        return (tuple(x.shape), x.dtype, str(x.device), extra, _SLOT[0], weights)
 
     def __call__(self, x, extra=None):
         usable = (_ENABLED and not self.disabled and x.is_cuda and not self.module.training

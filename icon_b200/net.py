@@ -261,8 +261,9 @@ class HGPIFuNet(BasePIFuNet):
         features_G = []
         if self.prior_type == "icon":
             if self.use_filter:
-                features_F = self.F_filter(in_filter[:, self.channels_filter[0]])
-                features_B = self.F_filter(in_filter[:, self.channels_filter[1]])
+                from .graphs import run_pair
+                xF, xB = in_filter[:, self.channels_filter[0]].contiguous(), in_filter[:, self.channels_filter[1]].contiguous()
+                features_F, features_B = run_pair(lambda: self.F_filter(xF), lambda: self.F_filter(xB))
             else:
                 features_F = [in_filter[:, self.channels_filter[0]]]
                 features_B = [in_filter[:, self.channels_filter[1]]]
