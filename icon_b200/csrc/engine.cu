@@ -73,59 +73,6 @@ __global__ void __launch_bounds__(256) k_grid_upsample(const float *__restrict__
     }
 }
 
-// Last level (seg3d_lossless.py:186-203: interpolation only, no masks): 8 bytes written per byte read, so the kernel
-// is a store stream.  One block = UP_Y consecutive output rows of one z plane = ONE contiguous span of UP_Y * Ro floats
-// in memory: the (<= UP_Y / 2 + 2) x 2 contributing input rows are staged in shared memory with coalesced loads,
-// every thread computes its outputs from there (same operations in the same order as k_grid_upsample: bit-identical),
-// and the span goes out as 128-bit stores from its first 16-byte-aligned element (scalar head / tail).
-constexpr int UP_Y = 8;
-__global__ void __launch_bounds__(256) k_grid_upsample_rows(const float *__restrict__ in, int Ri, float *__restrict__ out) {
-    extern __shared__ float sm[];
-    const int Ro = 2 * Ri - 1;
-    const int z = blockIdx.y, y_begin = blockIdx.x * UP_Y, ny = min(UP_Y, Ro - y_begin);
-    const int z0 = z >> 1;
-    const bool oz = z & 1;
-    const int iy0 = y_begin >> 1, iy1 = min((y_begin + ny - 1 + 1) >> 1, Ri - 1);     // input rows iy0 .. iy1
-    const int nrow = iy1 - iy0 + 1;
-    float *rows0 = sm, *rows1 = sm + (UP_Y / 2 + 2) * Ri, *obuf = sm + 2 * (UP_Y / 2 + 2) * Ri;
-    const size_t RR = (size_t)Ri * Ri;
-    for (int t = threadIdx.x; t < nrow * Ri; t += blockDim.x) {
-        const int r = t / Ri, i = t - r * Ri;
-        rows0[t] = in[z0 * RR + (size_t)(iy0 + r) * Ri + i];
-        if (oz) rows1[t] = in[(z0 + 1) * RR + (size_t)(iy0 + r) * Ri + i];
-    }
-    __syncthreads();
-    const int total = ny * Ro;
-    for (int t = threadIdx.x; t < total; t += blockDim.x) {
-        const int yl = t / Ro, x = t - yl * Ro;
-        const int y = y_begin + yl;
-        const bool oy = y & 1, ox = x & 1;
-        const int r0 = (y >> 1) - iy0, i = x >> 1, i1 = min(i + 1, Ri - 1);
-        const float *p00 = rows0 + r0 * Ri, *p01 = p00 + (oy ? Ri : 0);
-        float v = ox ? half_sum(p00[i], p00[i1]) : p00[i];
-        if (oy) v = half_sum(v, ox ? half_sum(p01[i], p01[i1]) : p01[i]);
-        if (oz) {
-            const float *p10 = rows1 + r0 * Ri, *p11 = p10 + (oy ? Ri : 0);
-            float v2 = ox ? half_sum(p10[i], p10[i1]) : p10[i];
-            if (oy) v2 = half_sum(v2, ox ? half_sum(p11[i], p11[i1]) : p11[i]);
-            v = half_sum(v, v2);
-        }
-        obuf[t] = v;
-    }
-    __syncthreads();
-    float *dst = out + ((size_t)z * Ro + y_begin) * Ro;
-    const int head = (int)(((16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15) >> 2);   // floats until 16-byte alignment
-    const int h = min(head, total);
-    if ((int)threadIdx.x < h) dst[threadIdx.x] = obuf[threadIdx.x];
-    const int nvec = (total - h) >> 2;
-    for (int t = threadIdx.x; t < nvec; t += blockDim.x) {
-        const int e = h + 4 * t;
-        *reinterpret_cast<float4 *>(dst + e) = make_float4(obuf[e], obuf[e + 1], obuf[e + 2], obuf[e + 3]);
-    }
-    const int tail0 = h + 4 * nvec;
-    if ((int)threadIdx.x < total - tail0) dst[tail0 + threadIdx.x] = obuf[tail0 + threadIdx.x];
-}
-
 // ---------------------------------------------------------------- separable box dilation
 // axis 0: along x ([z][y][x] -> [z][y][x]); axis 1: along y; axis 2: along z, written as [x][y][z]
 template <int AXIS>
@@ -232,13 +179,6 @@ extern "C" int icon_grid_upsample(const float *occ_in, const uint8_t *done_in, i
     cudaStream_t stream = (cudaStream_t)stream_;
     ICON_CHECK_ARG(occ_in && occ_out && R_in >= 2 && R_in <= 32768, "icon_grid_upsample: bad argument (R_in=%d)", R_in);
     const int Ro = 2 * R_in - 1;
-    const size_t smem = ((size_t)2 * (UP_Y / 2 + 2) * R_in + (size_t)UP_Y * Ro) * sizeof(float);
-    if (!boundary && !done_out && smem <= 48 * 1024) {          // last level: values only
-        dim3 grid((unsigned)((Ro + UP_Y - 1) / UP_Y), (unsigned)Ro);
-        k_grid_upsample_rows<<<grid, 256, smem, stream>>>(occ_in, R_in, occ_out);
-        ICON_LAUNCHED();
-        return ICON_OK;
-    }
     dim3 grid((unsigned)(((int64_t)Ro * R_in + 255) / 256), Ro);
     k_grid_upsample<<<grid, 256, 0, stream>>>(occ_in, done_in, R_in, balance, occ_out, boundary, done_out);
     ICON_LAUNCHED();
