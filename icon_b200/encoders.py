@@ -108,13 +108,19 @@ class HourGlass(nn.Module):
 
     def forward_nhwc(self, level, inp):
         from . import nhwc as T
-        up1 = self._modules["b1_" + str(level)].forward_nhwc(inp)
-        low1 = self._modules["b2_" + str(level)].forward_nhwc(T.avg_pool2(inp.dense()))
-        if level > 1:
-            low2 = self.forward_nhwc(level - 1, low1)
-        else:
-            low2 = self._modules["b2_plus_" + str(level)].forward_nhwc(low1)
-        low3 = self._modules["b3_" + str(level)].forward_nhwc(low2)
+        from .graphs import run_pair
+
+        def low_path():
+            low1 = self._modules["b2_" + str(level)].forward_nhwc(T.avg_pool2(inp.dense()))
+            if level > 1:
+                low2 = self.forward_nhwc(level - 1, low1)
+            else:
+                low2 = self._modules["b2_plus_" + str(level)].forward_nhwc(low1)
+            return self._modules["b3_" + str(level)].forward_nhwc(low2)
+
+        # the skip branch (one ConvBlock at full resolution) and the whole low-resolution path are independent until
+        # the final add: two streams (inside the captured graph: two parallel branches)
+        low3, up1 = run_pair(low_path, lambda: self._modules["b1_" + str(level)].forward_nhwc(inp))
         return T.bicubic_up2_add(low3.dense(), up1.dense())
 
 

@@ -35,33 +35,41 @@ def concurrent(flag=None):
 
 
 def run_pair(fn_a, fn_b):
-    """(fn_a(), fn_b()) -- fn_b on a side stream when concurrency is on and the tensors live on a GPU.  The results
-    are safe to use on the current stream afterwards (the side stream is joined, its outputs are marked as used
-    by the current stream for the caching allocator)."""
-    if not (_CONCURRENT and torch.cuda.is_available()) or torch.cuda.is_current_stream_capturing():
+    """(fn_a(), fn_b()) -- fn_b on a side stream forked from the current one and joined afterwards, when concurrency
+    is on.  Works eagerly and INSIDE a CUDA-graph capture (the fork / join become graph edges, so a replay runs the two
+    branches side by side).  Nesting is fine: every stream has its own side stream.  Discipline that keeps the caching
+    allocator safe without record_stream during capture: a side stream always first waits for its parent, and the
+    parent always joins it before using the results."""
+    if not (_CONCURRENT and torch.cuda.is_available()):
         return fn_a(), fn_b()
-    main = torch.cuda.current_stream()
-    key = main.device_index
+    cur = torch.cuda.current_stream()
+    capturing = torch.cuda.is_current_stream_capturing()
+    key = (cur.device_index, cur.cuda_stream)
     side = _SIDE.get(key)
     if side is None:
-        side = _SIDE[key] = torch.cuda.Stream(device=key)
-    side.wait_stream(main)
-    _SLOT[0] = 1
+        side = _SIDE[key] = torch.cuda.Stream(device=cur.device_index)
+    side.wait_stream(cur)
+    prev, _SLOT[0] = _SLOT[0], 1
     try:
         with torch.cuda.stream(side):
             b = fn_b()
     finally:
-        _SLOT[0] = 0
+        _SLOT[0] = prev
     a = fn_a()
-    main.wait_stream(side)
+    cur.wait_stream(side)
 
     def mark(t):
         if isinstance(t, torch.Tensor) and t.is_cuda:
-            t.record_stream(main)
+            t.record_stream(cur)
         elif isinstance(t, (list, tuple)):
             for u in t:
                 mark(u)
-    mark(b)
+        elif hasattr(t, "__dict__"):                     # nhwc.Raw / Operand: tensors in attributes
+            for u in vars(t).values():
+                if isinstance(u, torch.Tensor) and u.is_cuda:
+                    u.record_stream(cur)
+    if not capturing:
+        mark(b)
     return a, b
 
 
