@@ -58,16 +58,24 @@ class ConvBlock(nn.Module):
         from . import nhwc as T
         c1, c2, c3 = self.conv1.out_channels, self.conv2.out_channels, self.conv3.out_channels
         y = torch.empty(x.N, x.H, x.W, c1 + c2 + c3, dtype=torch.float32, device=x.t.device)
-        op, _ = T.act(x, T.finalize(x, self.bn1), relu=True)
-        r1 = T.conv(op, self.conv1, out=y, co_off=0)
-        op, _ = T.act(r1, T.finalize(r1, self.bn2), relu=True)
-        r2 = T.conv(op, self.conv2, out=y, co_off=c1)
-        op, _ = T.act(r2, T.finalize(r2, self.bn3), relu=True)
-        T.conv(op, self.conv3, out=y, co_off=c1 + c2, stats=False)
-        if self.downsample is not None:
+        def main_chain():
+            op, _ = T.act(x, T.finalize(x, self.bn1), relu=True)
+            r1 = T.conv(op, self.conv1, out=y, co_off=0)
+            op, _ = T.act(r1, T.finalize(r1, self.bn2), relu=True)
+            r2 = T.conv(op, self.conv2, out=y, co_off=c1)
+            op, _ = T.act(r2, T.finalize(r2, self.bn3), relu=True)
+            T.conv(op, self.conv3, out=y, co_off=c1 + c2, stats=False)
+            return y
+
+        def projection():
             op, _ = T.act(x, T.finalize(x, self.bn4), relu=True)
-            residual = T.conv(op, self.downsample[2], stats=False).t
+            return T.conv(op, self.downsample[2], stats=False).t
+
+        if self.downsample is not None:
+            from .graphs import run_pair
+            _, residual = run_pair(main_chain, projection)      # the 1x1 projection is independent of the 3-conv chain
         else:
+            main_chain()
             residual = x.dense()
         return T.add(y, residual)
 
@@ -199,9 +207,12 @@ class HGFilter(nn.Module):
                 tmp_out = T.conv(op_ll, self._modules["l" + str(i)], stats=False)
                 outputs.append(T.to_nchw(tmp_out))
                 if i < self.num_modules - 1:
-                    llb = T.conv(op_ll, self._modules["bl" + str(i)], stats=False)
-                    op_t, _ = T.act(tmp_out)
-                    t2 = T.conv(op_t, self._modules["al" + str(i)], stats=False)
+                    from .graphs import run_pair
+
+                    def back(tmp_out=tmp_out, i=i):
+                        op_t, _ = T.act(tmp_out)
+                        return T.conv(op_t, self._modules["al" + str(i)], stats=False)
+                    llb, t2 = run_pair(lambda i=i, op_ll=op_ll: T.conv(op_ll, self._modules["bl" + str(i)], stats=False), back)
                     previous = T.add(previous.dense(), llb.t, t2.t)
         return outputs
 
