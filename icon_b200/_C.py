@@ -36,6 +36,7 @@ _SIGS = {
     "icon_sdf_only": (_i, [_vp, _i64, _i64, _i64, _vp, _vp, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "icon_sdf_bruteforce": (_i, [_vp, _i64, _i64, _i64, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "icon_mlp_only": (_i, [_vp, _i, _i64, _vp, _vp, _vp, _vp]),
+    "icon_display": (_i, [_vp, _i, _vp, _vp]),
     "icon_grid_upsample": (_i, [_vp, _vp, _i, _f, _vp, _vp, _vp, _vp]),
     "icon_grid_dilate": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
     "icon_compact_workspace_bytes": (_sz, [_i]),

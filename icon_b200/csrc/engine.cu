@@ -174,6 +174,49 @@ static Box make_box(const float *bmin, const float *bmax) {
 
 using namespace icon;
 
+// ---------------------------------------------------------------- 4-view normal preview (Seg3dLossless.display)
+// seg3d_lossless.py:497-581 (find_vertices / render_normal / display), what ICON.render_func shows during training:
+// for each of the views front / left / right / back and each image column (a, b): the FIRST voxel along the view axis
+// whose occupancy exceeds 0.5; its colour is the normalised backward finite difference (step 2, clamped at the border)
+// of the occupancy along (a, b, c), mapped to [0, 1]; columns that hit nothing stay white.  out: uint8 [R][4 R][3].
+// View v reads the volume [z][y][x] as s(a, b, c) = occ[R-1-c][b][a] (front), occ[a][b][R-1-c] (left),
+// occ[a][b][c] (right), occ[c][b][a] (back) -- the reference's permute / flip chains written out.
+__global__ void k_display(const float *__restrict__ occ, int R, uint8_t *__restrict__ out) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y, view = blockIdx.z;
+    if (a >= R) return;
+    const size_t RR = (size_t)R * R;
+    auto S = [&](int aa, int bb, int cc) -> float {
+        switch (view) {
+            case 0: return occ[(size_t)(R - 1 - cc) * RR + (size_t)bb * R + aa];      // front
+            case 1: return occ[(size_t)aa * RR + (size_t)bb * R + (R - 1 - cc)];      // left
+            case 2: return occ[(size_t)aa * RR + (size_t)bb * R + cc];                // right
+            default: return occ[(size_t)cc * RR + (size_t)bb * R + aa];               // back
+        }
+    };
+    float r = 1.f, g = 1.f, bl = 1.f;
+    for (int c = 0; c < R; ++c) {
+        const float v1 = S(a, b, c);
+        if (!(v1 > 0.5f)) continue;
+        const float nx = S(max(a - 2, 0), b, c) - v1, ny = S(a, max(b - 2, 0), c) - v1, nz = S(a, b, max(c - 2, 0)) - v1;
+        const float nrm = sqrtf(nx * nx + ny * ny + nz * nz);
+        r = fminf(fmaxf((nx / nrm + 1.f) / 2.f, 0.f), 1.f);
+        g = fminf(fmaxf((ny / nrm + 1.f) / 2.f, 0.f), 1.f);
+        bl = fminf(fmaxf((nz / nrm + 1.f) / 2.f, 0.f), 1.f);
+        break;
+    }
+    uint8_t *px = out + ((size_t)b * 4 * R + (size_t)view * R + a) * 3;
+    px[0] = (uint8_t)(r * 255.0f); px[1] = (uint8_t)(g * 255.0f); px[2] = (uint8_t)(bl * 255.0f);
+}
+
+extern "C" int icon_display(const float *occ, int R, uint8_t *out, icon_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    ICON_CHECK_ARG(occ && out && R >= 3 && R <= 4096, "icon_display: bad argument (R=%d)", R);
+    dim3 grid((unsigned)((R + 127) / 128), (unsigned)R, 4);
+    k_display<<<grid, 128, 0, stream>>>(occ, R, out);
+    ICON_LAUNCHED();
+    return ICON_OK;
+}
+
 extern "C" int icon_grid_upsample(const float *occ_in, const uint8_t *done_in, int R_in, float balance,
                                   float *occ_out, uint8_t *boundary, uint8_t *done_out, icon_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;

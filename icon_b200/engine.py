@@ -102,48 +102,9 @@ class Seg3dLossless(nn.Module):
         v_cpu._icon_device_mesh = (verts, faces)      # lets icon_b200.mesh.clean_mesh skip the upload (apps/ICON.py:753-756)
         return v_cpu, f_cpu
 
-    # ---- training-time preview (apps/ICON.py:694-727 render_func); off the inference hot path, plain torch ops
-    def find_vertices(self, sdf, direction="front"):
-        """seg3d_lossless.py:498-552: first-hit depth along one axis + finite-difference normal."""
-        resolution = sdf.size(2)
-        if direction == "left":
-            sdf = sdf.permute(2, 1, 0)
-        elif direction == "back":
-            sdf = sdf.flip(0)
-        elif direction == "right":
-            sdf = sdf.flip(2).permute(2, 1, 0)
-        sdf_all = sdf.flip(0).permute(2, 1, 0)
-        inside = sdf_all > 0.5
-        grad_v = inside * torch.linspace(resolution, 1, steps=resolution, device=sdf.device)
-        grad_c = torch.ones_like(sdf_all) * torch.linspace(0, resolution - 1, steps=resolution, device=sdf.device)
-        max_v, max_c = grad_v.max(dim=2)
-        shadow = grad_c > max_c.view(resolution, resolution, 1)
-        keep = inside & (~shadow)
-        p1 = keep.nonzero(as_tuple=False).t()
-        p2 = p1.clone(); p2[2, :] = (p2[2, :] - 2).clamp(0, resolution)
-        p3 = p1.clone(); p3[1, :] = (p3[1, :] - 2).clamp(0, resolution)
-        p4 = p1.clone(); p4[0, :] = (p4[0, :] - 2).clamp(0, resolution)
-        v1 = sdf_all[p1[0], p1[1], p1[2]]
-        v2 = sdf_all[p2[0], p2[1], p2[2]]
-        v3 = sdf_all[p3[0], p3[1], p3[2]]
-        v4 = sdf_all[p4[0], p4[1], p4[2]]
-        X, Y = p1[0].long(), p1[1].long()
-        Z = p2[2].float() * (0.5 - v1) / (v2 - v1) + p1[2].float() * (v2 - 0.5) / (v2 - v1)
-        Z = Z.clamp(0, resolution)
-        norm = torch.stack([v4 - v1, v3 - v1, v2 - v1], dim=1)
-        norm = norm / torch.norm(norm, p=2, dim=1, keepdim=True)
-        return X, Y, Z, norm
-
-    def render_normal(self, resolution, X, Y, Z, norm):
-        """seg3d_lossless.py:554-564."""
-        image = torch.ones((1, 3, resolution, resolution), dtype=torch.float32, device=norm.device)
-        color = ((norm + 1) / 2.0).clamp(0, 1)
-        image[0, :, Y, X] = color.t()
-        return image
-
     def display(self, sdf):
-        """seg3d_lossless.py:566-581: 4-view normal splat, uint8 [R, 4R, 3]."""
-        R = int(self.resolutions[-1, -1])
-        views = [self.render_normal(R, *self.find_vertices(sdf, d)) for d in ("front", "left", "right", "back")]
-        image = torch.cat(views, axis=3).detach().cpu().numpy()[0].transpose(1, 2, 0) * 255.0
-        return np.uint8(image)
+        """seg3d_lossless.py:566-581 (with find_vertices / render_normal, :497-564): uint8 [R, 4R, 3] preview of the
+        volume from the front / left / right / back -- first voxel above 0.5 along the view axis, coloured by the
+        normalised finite-difference gradient; one kernel (icon_display), pinned to the reference's own output
+        (tests/golden/engine.npz: `display`)."""
+        return ops.display(sdf)

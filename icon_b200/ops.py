@@ -318,6 +318,18 @@ def grid_count_above(occ, balance):
     return int(cnt.item())
 
 
+def display(occ):
+    """Seg3dLossless.display on the device: occ [R,R,R] -> uint8 ndarray [R, 4R, 3] (include/icon_b200.h: icon_display)."""
+    _need_cuda(occ)
+    o = occ.detach().float().contiguous()
+    R = o.shape[0]
+    if o.dim() != 3 or not (o.shape[1] == R and o.shape[2] == R):
+        raise _C.IconError(f"display: occupancy grid must be [R,R,R], got {tuple(o.shape)}")
+    out = torch.empty(R, 4 * R, 3, dtype=torch.uint8, device=o.device)
+    check(lib.icon_display(_p(o), R, _p(out), _stream()), "icon_display")
+    return out.cpu().numpy()
+
+
 # --------------------------------------------------------------------------- marching cubes
 def marching_cubes(occ, iso=0.5, order="edge"):
     """export_mesh on the device: occ [R,R,R] -> (verts [Nv,3] f32|f64 xyz, faces [Nf,3] i64), CUDA.

@@ -134,6 +134,8 @@ int icon_mlp_only(const float *feature, int c0, int64_t N, const float *mlp_pack
  * (occupancy and (occ>balance) mask) fused with is_boundary = 0<valid<1 and with the
  * carry-over of the already-evaluated set (coords_accum*2).  R_out = 2*R_in-1.
  * boundary/done_out may be NULL (last level: upsample only, :186-203). */
+int icon_display(const float *occ, int R, uint8_t *out /* [R][4R][3] */, icon_stream_t stream);   /* Seg3dLossless.display:
+   first-hit + finite-difference normal preview, views front | left | right | back (seg3d_lossless.py:497-581) */
 int icon_grid_upsample(const float *occ_in, const uint8_t *done_in, int R_in, float balance,
                        float *occ_out, uint8_t *boundary, uint8_t *done_out,
                        icon_stream_t stream);

@@ -103,6 +103,7 @@ def main():
             occ = engine()
         eng[f"{tag}_res"] = np.asarray(res)
         eng[f"{tag}_occ"] = occ.numpy()
+        eng[f"{tag}_display"] = engine.display(occ)            # reference's own 4-view preview of its own volume (uint8)
         eng[f"{tag}_ncalls"] = np.asarray(len(log))
         for i, p in enumerate(log):
             eng[f"{tag}_pts{i}"] = p.numpy()

@@ -64,6 +64,24 @@ def test_engine_grid_identical_to_oracle_engine():
     assert torch.equal(occ, ref)                      # bit-identical grid (same field values in)
 
 
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_display_matches_reference_preview(tag, golden_dir):
+    """Seg3dLossless.display (4-view first-hit normal preview) as ONE kernel vs the uint8 image the reference's own
+    find_vertices / render_normal / display produced for its own volume (tests/golden/engine.npz)."""
+    dev = _cuda()
+    from icon_b200.engine import Seg3dLossless
+    g = np.load(os.path.join(golden_dir, "engine.npz"))
+    res = [int(r) for r in g[f"{tag}_res"]]
+    eng = Seg3dLossless(query_func=None, b_min=[[-1.0, 1.0, -1.0]], b_max=[[1.0, -1.0, 1.0]], resolutions=res,
+                        align_corners=True, balance_value=0.5, faster=True).to(dev)
+    img = eng.display(torch.from_numpy(g[f"{tag}_occ"]).to(dev))
+    ref = g[f"{tag}_display"]
+    assert img.dtype == np.uint8 and img.shape == ref.shape == (res[-1], 4 * res[-1], 3)
+    diff = np.abs(img.astype(np.int16) - ref.astype(np.int16))
+    assert diff.max() <= 1                                  # float rounding of the normalisation at a truncation boundary
+    assert (diff > 0).mean() < 0.01 and (ref != 255).mean() > 0.05
+
+
 def test_engine_returns_none_on_empty_volume():
     dev = _cuda()
     from icon_b200.engine import Seg3dLossless

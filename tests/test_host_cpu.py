@@ -141,17 +141,13 @@ def test_oracle_marching_cubes_is_watertight_and_matches_analytic_sphere():
     assert abs(abs(vol) - 4.0 / 3.0 * np.pi * 0.6 ** 3) < 2e-2
 
 
-def test_display_preview_runs_on_cpu_tensor():
-    """R14 (training preview): plain torch restatement of seg3d_lossless.py:498-581, shape/dtype contract."""
-    import numpy as np
+def test_display_refuses_cpu_tensors():
+    """R14 (training preview) is a kernel now (icon_display): like every op it has no CPU path."""
+    from icon_b200 import _C
     from icon_b200.engine import Seg3dLossless
     eng = Seg3dLossless(None, [[-1.0, 1, -1]], [[1.0, -1, 1]], resolutions=[17, 33], align_corners=True, faster=True)
-    a = torch.linspace(-1, 1, 33)
-    z, y, x = torch.meshgrid(a, a, a, indexing="ij")
-    occ = 0.5 + (0.6 - torch.sqrt(x * x + y * y + z * z))
-    img = eng.display(occ)
-    assert img.shape == (33, 4 * 33, 3) and img.dtype == np.uint8
-    assert (img != 255).any()
+    with pytest.raises(_C.IconError):
+        eng.display(torch.zeros(33, 33, 33))
 
 
 def test_source_cache_is_keyed_on_tensor_identity_and_version():
