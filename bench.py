@@ -237,6 +237,11 @@ def _fix_omp_threads():
                 n = max(1, min(n, q // p))
         except Exception:
             pass
+    if "TORCHELASTIC_RUN_ID" in os.environ or "LOCAL_RANK" in os.environ:
+        # torchrun pins OMP_NUM_THREADS=1 for every rank unless the user set it; the CPU arm runs on rank 0 alone and is
+        # specified to use all the host threads it can
+        if os.environ.get("OMP_NUM_THREADS", "1") == "1":
+            os.environ["OMP_NUM_THREADS"] = str(n)
     os.environ.setdefault("OMP_NUM_THREADS", str(n))
     return n
 
@@ -512,7 +517,6 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")          # keep NCCL's version banner off stdout: ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     from icon_b200 import _C, net, synthetic as S, dist as D
