@@ -8,7 +8,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libicon_b200.so")
+LIB_PATH = os.environ.get("ICON_B200_LIB") or os.path.join(_HERE, "libicon_b200.so")   # override: diagnostics builds only
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(

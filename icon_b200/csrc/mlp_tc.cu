@@ -11,19 +11,26 @@
 // One persistent CTA per SM, 128 query points (= 128 TMEM lanes) per tile, 448 threads:
 //   warp 0      weight producer: 1-D bulk copies (cp.async.bulk, TMA engine) of host-pre-swizzled
 //               K-major SWIZZLE_128B tiles from L2 into a 2 x 64 KB ring, mbarrier complete_tx
-//   warp 1      MMA issuer (one elected lane): tcgen05.mma.cta_group::1.kind::f16, M=128
+//               (per tile: 8 layer-1 K-chunks and 2 pairs of layer-2 K-chunks; layer 0 and the x0 tail of
+//               layer 2 stay resident in shared memory)
+//   warp 1      MMA issuer, all 32 lanes converged, tcgen05.mma.cta_group::1.kind::f16 M=128 under elect.sync
+//               (operands in uniform registers); the barriers of chunk j+1 are checked while chunk j still has
+//               MMAs to issue, so the tensor pipe never drains between chunks
 //   warps 2-9   workers, one TMEM lane (= query point) per thread, two threads per lane:
 //               per 64-column chunk of layer 0: tcgen05.ld -> +bias -> LeakyReLU -> hi/lo fp16 ->
 //               tcgen05.st as the A operand (in TMEM) of layer 1; same for layer 1 -> layer 2 (in 4
-//               K-chunks so layer 2 starts early); layer 3 (141 -> 1) as an fp32 dot in registers.
-//   warps 10-13 gather: one query point per thread; the 16 input features of tile i+1 (bilinear /
-//               trilinear samples, SMPL record, outlier rule) are produced and published as the
-//               double-buffered x0 operand while tile i is in the tensor pipe.
+//               K-chunks so layer 2 starts early).  They go straight on to the next tile.
+//   warps 10-13 gather + epilogue, one query point per thread: the 16 input features of tile i+1 (bilinear /
+//               trilinear samples, SMPL record, outlier rule) are produced and published as the double-buffered
+//               x0 operand while tile i is in the tensor pipe; then layer 3 (141 -> 1) of tile i as an fp32 dot
+//               over the layer-2 accumulator, off the critical path of the next tile (which only waits until
+//               the accumulator has been read).
 // Layer-0 chunks are issued two ahead of the layer-1 chunk that consumes them, so the tensor pipe
 // always has queued work while the workers convert.  TMEM map (512 columns):
 //   [0,256) layer-1 accumulator (later [0,128) layer-2 accumulator)
 //   [256,384) 2 x (hi 32 | lo 32) A-operand chunks of layer 1   } later: layer-1 activations
 //   [384,512) 2 x 64 layer-0 accumulator chunks                 } hi [256,384), lo [384,512)
+// Where the cycles of a tile go was measured with tools/mlp_timeline.py (profiles/r2_summary.md).
 // Operand layouts were verified on hardware with tools/umma_probe.cu.
 #include <cuda_fp16.h>
 
@@ -52,13 +59,13 @@ constexpr int SM_X0H = SM_W0 + 32768;             // 2 x 4096  A tile of x0 (hi)
 constexpr int SM_X0L = SM_X0H + 8192;             // 2 x 4096
 constexpr int SM_X0F = SM_X0L + 8192;             // 2 x [16][128] fp32
 constexpr int SM_F32 = SM_X0F + 2 * 8192;         // biases etc.
-constexpr int SM_PART = SM_F32 + TCB_F32_FLOATS * 4;   // [128] fp32 layer-3 partials
-constexpr int SM_BAR = SM_PART + 512;             // 24 mbarriers
+constexpr int SM_W2T = (SM_F32 + TCB_F32_FLOATS * 4 + 127) / 128 * 128;   // 8192: x0 tail of layer 2 (hi 4096 | lo 4096), resident
+constexpr int SM_BAR = SM_W2T + 8192;             // 24 mbarriers
 constexpr int SM_MISC = SM_BAR + 24 * 8;
 constexpr int SM_TOTAL = SM_MISC + 64;
 constexpr int TC_SMEM_BYTES = SM_TOTAL + 1024;    // slack for manual 1024-B alignment
 
-enum { B_WFULL0 = 0, B_WFULL1, B_WEMPTY0, B_WEMPTY1, B_X0R0, B_X0R1, B_X0F0, B_X0F1, B_ACC0F0, B_ACC0F1, B_A0F0, B_A0F1,
+enum { B_WFULL0 = 0, B_WFULL1, B_WEMPTY0, B_WEMPTY1, B_X0R0, B_X0R1, B_ACC2E, B_SPARE, B_ACC0F0, B_ACC0F1, B_A0F0, B_A0F1,
        B_A0E0, B_A0E1, B_ACC1, B_ACT1_0, B_ACT1_1, B_ACT1_2, B_ACT1_3, B_ACC2, B_W0RDY };
 
 // TMEM columns
@@ -93,6 +100,15 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// One lane of a CONVERGED warp.  The MMA warp runs its whole loop on all 32 lanes and predicates only the tcgen05
+// instructions with this: their operands then stay in uniform registers.  (Issuing from inside `if (lane == 0)` made ptxas
+// build every descriptor in vector registers and wrap each UTCHMMA in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall:
+// ~90 clocks per issue against 32-128 clocks of execution, measured with tools/mlp_timeline.py.)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t p;
+    asm volatile("{\n.reg .pred q;\nelect.sync _|q, 0xffffffff;\nselp.b32 %0, 1, 0, q;\n}" : "=r"(p));
+    return p != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -116,6 +132,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t (&r)[32]) {
         : "r"(addr) : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t addr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,"
+        "%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st16(uint32_t addr, const uint32_t (&r)[16]) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(addr),
                  "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
@@ -160,6 +187,14 @@ __device__ __forceinline__ void act_split32(const uint32_t (&acc)[32], const flo
     }
 }
 
+#ifdef ICON_MLP_TIMELINE
+// diagnostics build only (tools/mlp_timeline.py): SM-clock stamps of one tile of one CTA
+__device__ long long g_tl[256];
+#define TL(slot) do { if (blockIdx.x == 3 && tcount == 6) g_tl[slot] = clock64(); } while (0)
+#else
+#define TL(slot) do { } while (0)
+#endif
+
 // MODE: 0 icon, 1 pifu, 2 pamir, 3 raw feature matrix
 template <int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_query_mlp_tc(QueryParams q, const uint8_t *__restrict__ blob) {
@@ -170,7 +205,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_query_mlp_tc(QueryParams q, c
     float *x0f = reinterpret_cast<float *>(sm + SM_X0F);
     const float *sf32 = reinterpret_cast<const float *>(sm + SM_F32);
     const float *sb0 = sf32, *sb1 = sf32 + 512, *sb2 = sf32 + 768, *sw3 = sf32 + 896, *sb3 = sf32 + 1040;
-    float *spart = reinterpret_cast<float *>(sm + SM_PART);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sm + SM_MISC);
     const uint32_t bar0 = base + SM_BAR;
     auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
@@ -182,8 +216,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_query_mlp_tc(QueryParams q, c
     if (tid == 0) {
         mbar_init(BAR(B_WFULL0), 1); mbar_init(BAR(B_WFULL1), 1);
         mbar_init(BAR(B_WEMPTY0), 1); mbar_init(BAR(B_WEMPTY1), 1);
-        mbar_init(BAR(B_X0R0), 128); mbar_init(BAR(B_X0R1), 128);      // gather warps -> MMA / workers
-        mbar_init(BAR(B_X0F0), 256); mbar_init(BAR(B_X0F1), 256);      // workers -> gather warps (buffer free)
+        mbar_init(BAR(B_X0R0), 128); mbar_init(BAR(B_X0R1), 128);      // gather warps -> MMA
+        mbar_init(BAR(B_ACC2E), 128); mbar_init(BAR(B_SPARE), 1);     // epilogue: layer-2 accumulator has been read
         mbar_init(BAR(B_ACC0F0), 1); mbar_init(BAR(B_ACC0F1), 1);
         mbar_init(BAR(B_A0F0), 256); mbar_init(BAR(B_A0F1), 256);
         mbar_init(BAR(B_A0E0), 1); mbar_init(BAR(B_A0E1), 1);
@@ -205,133 +239,177 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_query_mlp_tc(QueryParams q, c
         // ======================================================== weight producer
         if (lane == 0) {
             // resident: W0 (hi | lo) and the fp32 tail (biases, last layer)
-            mbar_expect_tx(BAR(B_W0RDY), 32768 + TCB_F32_FLOATS * 4);
+            mbar_expect_tx(BAR(B_W0RDY), 32768 + TCB_F32_FLOATS * 4 + 8192);
             bulk_g2s(base + SM_W0, blob + TCB_W0, 32768, BAR(B_W0RDY));
             bulk_g2s(base + SM_F32, blob + TCB_F32, TCB_F32_FLOATS * 4, BAR(B_W0RDY));
+            bulk_g2s(base + SM_W2T, blob + TCB_W2T, 8192, BAR(B_W0RDY));
             uint32_t cnt = 0;
             for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                for (int i = 0; i < 13; ++i) {
+                for (int i = 0; i < 10; ++i) {           // 8 K-chunks of layer 1, then layer 2 two K-chunks at a time
                     const uint32_t s = cnt & 1, ph = (cnt >> 1) & 1;
                     mbar_wait(BAR(B_WEMPTY0 + s), ph ^ 1);
-                    const uint8_t *src;
-                    uint32_t bytes;
-                    if (i < 8) { src = blob + TCB_W1 + (size_t)i * 65536; bytes = 65536; }
-                    else if (i < 12) { src = blob + TCB_W2 + (size_t)(i - 8) * 32768; bytes = 32768; }
-                    else { src = blob + TCB_W2T; bytes = 8192; }
-                    mbar_expect_tx(BAR(B_WFULL0 + s), bytes);
-                    bulk_g2s(base + SM_STAGE + s * 65536, src, bytes, BAR(B_WFULL0 + s));
+                    const uint8_t *src = i < 8 ? blob + TCB_W1 + (size_t)i * 65536 : blob + TCB_W2 + (size_t)(i - 8) * 65536;
+                    mbar_expect_tx(BAR(B_WFULL0 + s), 65536);
+                    bulk_g2s(base + SM_STAGE + s * 65536, src, 65536, BAR(B_WFULL0 + s));
                     ++cnt;
                 }
             }
         }
     } else if (warp == 1) {
-        // ======================================================== MMA issuer
-        if (lane == 0) {
+        // ======================================================== MMA issuer (all 32 lanes converged; see elect_one)
+        {
             constexpr uint32_t ID64 = idesc_f16(128, 64), ID256 = idesc_f16(128, 256), ID128 = idesc_f16(128, 128);
+            const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);      // provably warp-uniform
             const uint64_t dx0h0 = desc_nosw(base + SM_X0H, 2048, 128), dx0l0 = desc_nosw(base + SM_X0L, 2048, 128);
             const uint64_t dw0h = desc_nosw(base + SM_W0, 8192, 128), dw0l = desc_nosw(base + SM_W0 + 16384, 8192, 128);
-            uint32_t ph_x0[2] = {0, 0}, ph_a0f[2] = {0, 0}, ph_act1 = 0, cnt = 0, tcount = 0;
+            uint32_t ph_x0 = 0, ph_a0f = 0, ph_act1 = 0, cnt = 0, tcount = 0;     // per-buffer phase bits
             uint64_t dx0h = dx0h0, dx0l = dx0l0;
             mbar_wait(BAR(B_W0RDY), 0);
             auto L0 = [&](int j) {
-                const uint32_t d = tmem + T_ACC0 + 64u * (uint32_t)(j & 1);
+                const uint32_t d = tm + T_ACC0 + 64u * (uint32_t)(j & 1);
                 const uint64_t o = (uint64_t)(j * 64);              // 64 rows = 8 groups x 128 B = 1024 B -> 64 units
-                mma_ss(d, dx0h, dw0h + o, ID64, 0);
-                mma_ss(d, dx0h, dw0l + o, ID64, 1);
-                mma_ss(d, dx0l, dw0h + o, ID64, 1);
-                tc_commit(BAR(B_ACC0F0 + (j & 1)));
+                if (elect_one()) {
+                    mma_ss(d, dx0h, dw0h + o, ID64, 0);
+                    mma_ss(d, dx0h, dw0l + o, ID64, 1);
+                    mma_ss(d, dx0l, dw0h + o, ID64, 1);
+                    tc_commit(BAR(B_ACC0F0 + (j & 1)));
+                }
+                __syncwarp();
             };
             for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
                 const uint32_t xb = tcount & 1;
                 dx0h = dx0h0 + (uint64_t)(xb * 4096 / 16);
                 dx0l = dx0l0 + (uint64_t)(xb * 4096 / 16);
-                mbar_wait(BAR(B_X0R0 + xb), ph_x0[xb]); ph_x0[xb] ^= 1;
+                if (lane == 0) TL(0);
+                mbar_wait(BAR(B_X0R0 + xb), (ph_x0 >> xb) & 1); ph_x0 ^= 1u << xb;
                 tc_fence_after();
+                if (lane == 0) TL(1);
                 L0(0);
                 L0(1);
-                for (int j = 0; j < 8; ++j) {
+                if (lane == 0) TL(2);
+                uint32_t s_cur = 0, s_nxt = 0;
+                auto wait_a0 = [&](int j) {
                     const int b = j & 1;
-                    mbar_wait(BAR(B_A0F0 + b), ph_a0f[b]); ph_a0f[b] ^= 1;
-                    const uint32_t s = cnt & 1;
-                    mbar_wait(BAR(B_WFULL0 + s), (cnt >> 1) & 1); ++cnt;
+                    mbar_wait(BAR(B_A0F0 + b), (ph_a0f >> b) & 1); ph_a0f ^= 1u << b;
+                    if (lane == 0) TL(32 + j);
+                };
+                auto wait_w = [&](int slot) {
+                    s_nxt = cnt & 1;
+                    mbar_wait(BAR(B_WFULL0 + s_nxt), (cnt >> 1) & 1); ++cnt;
                     tc_fence_after();
-                    const uint32_t a_hi = tmem + T_A0 + 64u * b, a_lo = a_hi + 32;
-                    const uint64_t bh = desc_sw128(base + SM_STAGE + s * 65536), bl = desc_sw128(base + SM_STAGE + s * 65536 + 32768);
+                    if (lane == 0) TL(slot);
+                };
+                auto l1_ks = [&](int j, int ks0, int ks1) {
+                    const int b = j & 1;
+                    const uint32_t a_hi = tm + T_A0 + 64u * b, a_lo = a_hi + 32;
+                    const uint64_t bh = desc_sw128(base + SM_STAGE + s_cur * 65536), bl = desc_sw128(base + SM_STAGE + s_cur * 65536 + 32768);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {
-                        mma_ts(tmem + T_ACC1, a_hi + 8 * ks, bh + 2 * ks, ID256, (j | ks) != 0);
-                        mma_ts(tmem + T_ACC1, a_hi + 8 * ks, bl + 2 * ks, ID256, 1);
-                        mma_ts(tmem + T_ACC1, a_lo + 8 * ks, bh + 2 * ks, ID256, 1);
+                        for (int ks = ks0; ks < ks1; ++ks) {
+                            mma_ts(tm + T_ACC1, a_hi + 8 * ks, bh + 2 * ks, ID256, (j | ks) != 0);
+                            mma_ts(tm + T_ACC1, a_hi + 8 * ks, bl + 2 * ks, ID256, 1);
+                            mma_ts(tm + T_ACC1, a_lo + 8 * ks, bh + 2 * ks, ID256, 1);
+                        }
+                        if (ks1 == 4) {
+                            tc_commit(BAR(B_WEMPTY0 + s_cur));
+                            tc_commit(BAR(B_A0E0 + b));
+                        }
                     }
-                    tc_commit(BAR(B_WEMPTY0 + s));
-                    tc_commit(BAR(B_A0E0 + b));
+                    __syncwarp();
+                };
+                auto l2_ks = [&](int c, int ks0, int ks1) {              // a weight stage holds K-chunks (c & ~1, c | 1)
+                    const uint32_t wb = base + SM_STAGE + s_cur * 65536 + (uint32_t)(c & 1) * 32768;
+                    const uint64_t bh = desc_sw128(wb), bl = desc_sw128(wb + 16384);
+                    if (elect_one()) {
+#pragma unroll
+                        for (int ks = ks0; ks < ks1; ++ks) {
+                            const uint32_t ah = tm + T_ACT1H + 32 * c + 8 * ks, al = tm + T_ACT1L + 32 * c + 8 * ks;
+                            mma_ts(tm + T_ACC2, ah, bh + 2 * ks, ID128, (c | ks) != 0);
+                            mma_ts(tm + T_ACC2, ah, bl + 2 * ks, ID128, 1);
+                            mma_ts(tm + T_ACC2, al, bh + 2 * ks, ID128, 1);
+                        }
+                        if (ks1 == 4 && (c & 1)) tc_commit(BAR(B_WEMPTY0 + s_cur));
+                    }
+                    __syncwarp();
+                };
+                wait_a0(0); wait_w(3); s_cur = s_nxt;
+                if (tcount) {                                  // the epilogue warps have read the previous tile's layer-2 accumulator
+                    mbar_wait(BAR(B_ACC2E), (tcount - 1) & 1);
+                    tc_fence_after();
+                }
+#pragma unroll 1
+                for (int j = 0; j < 8; ++j) {
+                    l1_ks(j, 0, 3);
+                    if (j < 7) { wait_a0(j + 1); wait_w(3 + 2 * (j + 1)); }      // chunk j+1, while chunk j still has MMAs to issue
+                    l1_ks(j, 3, 4);
                     if (j + 2 < 8) L0(j + 2);
+                    s_cur = s_nxt;
+                    if (lane == 0) TL(4 + 2 * j);
                 }
-                tc_commit(BAR(B_ACC1));
+                if (elect_one()) tc_commit(BAR(B_ACC1));
+                __syncwarp();
+                if (lane == 0) TL(19);
                 // ---- layer 2, K-chunk c as soon as the workers have converted it
-                for (int c = 0; c < 4; ++c) {
+                auto wait_act1 = [&](int c) {
                     mbar_wait(BAR(B_ACT1_0 + c), ph_act1);
-                    const uint32_t s = cnt & 1;
-                    mbar_wait(BAR(B_WFULL0 + s), (cnt >> 1) & 1); ++cnt;
                     tc_fence_after();
-                    const uint64_t bh = desc_sw128(base + SM_STAGE + s * 65536), bl = desc_sw128(base + SM_STAGE + s * 65536 + 16384);
-#pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {
-                        const uint32_t ah = tmem + T_ACT1H + 32 * c + 8 * ks, al = tmem + T_ACT1L + 32 * c + 8 * ks;
-                        mma_ts(tmem + T_ACC2, ah, bh + 2 * ks, ID128, (c | ks) != 0);
-                        mma_ts(tmem + T_ACC2, ah, bl + 2 * ks, ID128, 1);
-                        mma_ts(tmem + T_ACC2, al, bh + 2 * ks, ID128, 1);
-                    }
-                    tc_commit(BAR(B_WEMPTY0 + s));
-                }
+                    if (lane == 0) TL(40 + c);
+                };
+                wait_w(20); s_cur = s_nxt;
+                wait_act1(0);
+                l2_ks(0, 0, 3); wait_act1(1); l2_ks(0, 3, 4);
+                l2_ks(1, 0, 3); wait_act1(2); wait_w(22); l2_ks(1, 3, 4);
+                s_cur = s_nxt;
+                l2_ks(2, 0, 3); wait_act1(3); l2_ks(2, 3, 4);
+                l2_ks(3, 0, 4);
                 ph_act1 ^= 1;
                 {
-                    const uint32_t s = cnt & 1;
-                    mbar_wait(BAR(B_WFULL0 + s), (cnt >> 1) & 1); ++cnt;
-                    tc_fence_after();
-                    const uint64_t th = desc_nosw(base + SM_STAGE + s * 65536, 2048, 128);
-                    const uint64_t tl = desc_nosw(base + SM_STAGE + s * 65536 + 4096, 2048, 128);
-                    mma_ss(tmem + T_ACC2, dx0h, th, ID128, 1);
-                    mma_ss(tmem + T_ACC2, dx0h, tl, ID128, 1);
-                    mma_ss(tmem + T_ACC2, dx0l, th, ID128, 1);
-                    tc_commit(BAR(B_WEMPTY0 + s));
+                    const uint64_t th = desc_nosw(base + SM_W2T, 2048, 128), tl = desc_nosw(base + SM_W2T + 4096, 2048, 128);
+                    if (elect_one()) {
+                        mma_ss(tm + T_ACC2, dx0h, th, ID128, 1);
+                        mma_ss(tm + T_ACC2, dx0h, tl, ID128, 1);
+                        mma_ss(tm + T_ACC2, dx0l, th, ID128, 1);
+                        tc_commit(BAR(B_ACC2));
+                    }
+                    __syncwarp();
                 }
-                tc_commit(BAR(B_ACC2));
+                if (lane == 0) TL(25);
             }
         }
     } else if (warp < 10) {
         // ======================================================== workers (8 warps, 256 threads)
         const int q4 = warp & 3;                  // TMEM lane quarter this warp may touch
         const int h = (warp - 2) >> 2;            // which half of the columns
-        const int r = q4 * 32 + lane;             // row of the tile = TMEM lane
         const uint32_t tl = tmem + ((uint32_t)(q4 * 32) << 16);
-        uint32_t ph_acc0[2] = {0, 0}, ph_a0e[2] = {0, 0}, ph_acc1 = 0, ph_acc2 = 0, ph_x0[2] = {0, 0};
+        uint32_t ph_acc0 = 0, ph_a0e = 0, ph_acc1 = 0;      // per-buffer phase bits
         uint32_t tcount = 0;
-        mbar_wait(BAR(B_W0RDY), 0);               // biases / last layer are in shared memory
+        mbar_wait(BAR(B_W0RDY), 0);               // biases are in shared memory
         for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
-            const uint32_t xb = tcount & 1;
-            const int64_t pi = tile * TC_M + r;
-            const bool live = pi < q.N;
-            const float *xf = x0f + xb * (16 * TC_M);
             // ---------------- layer 0 chunks -> A operand of layer 1
+#pragma unroll 1
             for (int j = 0; j < 8; ++j) {
                 const int b = j & 1;
-                mbar_wait(BAR(B_ACC0F0 + b), ph_acc0[b]); ph_acc0[b] ^= 1;
+                mbar_wait(BAR(B_ACC0F0 + b), (ph_acc0 >> b) & 1); ph_acc0 ^= 1u << b;
                 tc_fence_after();
+                if (tid == 64) TL(64 + 4 * j);
                 uint32_t acc[32], hi[16], lo[16];
                 tmem_ld32(tl + T_ACC0 + 64u * b + 32u * h, acc);
+                if (tid == 64) TL(65 + 4 * j);
                 act_split32(acc, sb0 + 64 * j + 32 * h, hi, lo);
-                mbar_wait(BAR(B_A0E0 + b), ph_a0e[b] ^ 1); ph_a0e[b] ^= 1;
+                if (tid == 64) TL(66 + 4 * j);
+                mbar_wait(BAR(B_A0E0 + b), ((ph_a0e >> b) & 1) ^ 1); ph_a0e ^= 1u << b;
                 tc_fence_after();
                 tmem_st16(tl + T_A0 + 64u * b + 16u * h, hi);
                 tmem_st16(tl + T_A0 + 64u * b + 32u + 16u * h, lo);
                 tmem_st_wait();
                 tc_fence_before();
                 mbar_arrive(BAR(B_A0F0 + b));
+                if (tid == 64) TL(67 + 4 * j);
             }
             // ---------------- layer 1 accumulator -> A operand of layer 2, one 64-wide K-chunk at a time
             mbar_wait(BAR(B_ACC1), ph_acc1); ph_acc1 ^= 1;
             tc_fence_after();
+            if (tid == 64) TL(100);
 #pragma unroll 1
             for (int t = 0; t < 4; ++t) {
                 uint32_t acc[32], hi[16], lo[16];
@@ -342,54 +420,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_query_mlp_tc(QueryParams q, c
                 tmem_st_wait();
                 tc_fence_before();
                 mbar_arrive(BAR(B_ACT1_0 + t));
+                if (tid == 64) TL(101 + t);
             }
-            // ---------------- layer 2 accumulator -> layer 3 dot product
-            mbar_wait(BAR(B_ACC2), ph_acc2); ph_acc2 ^= 1;
-            tc_fence_after();
-            float part = 0.f;
-#pragma unroll 1
-            for (int t = 0; t < 2; ++t) {
-                uint32_t acc[32];
-                tmem_ld32(tl + T_ACC2 + 64u * h + 32u * t, acc);
-                const float *bb = sb2 + 64 * h + 32 * t, *ww = sw3 + 64 * h + 32 * t;
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    float v = __uint_as_float(acc[i]) + bb[i];
-                    v = fmaxf(v, 0.01f * v);
-                    part = fmaf(ww[i], v, part);
-                }
-            }
-            if (h == 1) spart[r] = part;
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (h == 0) {
-                // x0 of this tile was published by the gather warps (the MMA warp waited on the same barrier)
-                mbar_wait(BAR(B_X0R0 + xb), ph_x0[xb]);
-                if (live) {
-                    float s = part + spart[r];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) s = fmaf(sw3[128 + j], xf[j * TC_M + r], s);
-                    s += sb3[0];
-                    const float in_cube = (MODE == 3) ? 1.f : q.xyz4[pi].w;
-                    q.out[pi] = in_cube * s;
-                }
-            }
-            ph_x0[xb] ^= 1;
-            // this tile's TMEM reads are complete (wait::ld) and x0 buffer xb is no longer needed
-            tc_fence_before();
-            mbar_arrive(BAR(B_X0F0 + xb));
         }
     } else {
-        // ======================================================== gather warps (4 warps, one row per thread):
-        // features of tile i+1 are produced while tile i is in the tensor pipe
-        const int r = (warp - 10) * 32 + lane;
+        // ======================================================== gather + epilogue warps (4 warps, one row per thread)
+        const int q4 = warp & 3;
+        const int r = q4 * 32 + lane;             // row of the tile = TMEM lane this warp may touch
+        const uint32_t tl = tmem + ((uint32_t)(q4 * 32) << 16);
         const int c0 = q.c0;
-        uint32_t ph_free[2] = {0, 0};
-        uint32_t tcount = 0;
-        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
-            const uint32_t xb = tcount & 1;
+        uint32_t ph_acc2 = 0, tcount = 0;
+
+        // features of one tile -> x0 operand buffer xb (fp16 hi / lo tiles for the tensor pipe, fp32 copy for layer 3)
+        auto gather_tile = [&](int64_t tile, uint32_t xb) {
             const int64_t pi = tile * TC_M + r;
             const bool live = pi < q.N;
-            float f[16];
+            float f[16], in_cube = 1.f;
 #pragma unroll
             for (int j = 0; j < 16; ++j) f[j] = 0.f;
             if (live) {
@@ -397,6 +443,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_query_mlp_tc(QueryParams q, c
                     for (int j = 0; j < c0; ++j) f[j] = q.raw[(size_t)j * q.N + pi];
                 } else {
                     const float4 xyz = q.xyz4[pi];
+                    in_cube = xyz.w;
                     if (MODE == 0) {
                         const int d = q.C / 2;
                         const float4 *rp = (const float4 *)(q.rec + 8 * pi);
@@ -437,12 +484,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_query_mlp_tc(QueryParams q, c
                     }
                 }
             }
-            // buffer xb free? (workers finished the tile that used it, which implies its MMAs completed)
-            mbar_wait(BAR(B_X0F0 + xb), ph_free[xb] ^ 1); ph_free[xb] ^= 1;
+            // Buffer xb is free: its last reader was tile-2's x0 tail MMA and this thread's own epilogue of that tile.
             float *xf = x0f + xb * (16 * TC_M);
             uint32_t hi[8], lo[8];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) xf[j * TC_M + r] = f[j];
+            for (int j = 0; j < 15; ++j) xf[j * TC_M + r] = f[j];
+            xf[15 * TC_M + r] = in_cube;                      // c0 <= 13: row 15 is spare
 #pragma unroll
             for (int i = 0; i < 8; ++i) split2(f[2 * i], f[2 * i + 1], hi[i], lo[i]);
             const int off = (int)xb * 4096 + (r >> 3) * 128 + (r & 7) * 16;
@@ -452,6 +499,53 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_query_mlp_tc(QueryParams q, c
             *reinterpret_cast<uint4 *>(sm + SM_X0L + off + 2048) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(BAR(B_X0R0 + xb));
+        };
+        // 32 columns of layer 3: LeakyReLU(acc + b2) . w3
+        auto dot32 = [&](const uint32_t (&acc)[32], int col, float s) {
+            const float *bb = sb2 + col, *ww = sw3 + col;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                float v = __uint_as_float(acc[i]) + bb[i];
+                v = fmaxf(v, 0.01f * v);
+                s = fmaf(ww[i], v, s);
+            }
+            return s;
+        };
+
+        if ((int64_t)blockIdx.x < ntiles) gather_tile(blockIdx.x, 0);
+        mbar_wait(BAR(B_W0RDY), 0);               // b2 / w3 / b3 are in shared memory
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+            const uint32_t xb = tcount & 1;
+            if (tid == 320) TL(128);
+            if (tile + gridDim.x < ntiles) gather_tile(tile + gridDim.x, xb ^ 1);     // while this tile is in the tensor pipe
+            if (tid == 320) TL(131);
+            // ---------------- layer 3 of this tile
+            const int64_t pi = tile * TC_M + r;
+            const float *xf = x0f + xb * (16 * TC_M);
+            mbar_wait(BAR(B_ACC2), ph_acc2); ph_acc2 ^= 1;
+            tc_fence_after();
+            if (tid == 320) TL(132);
+            uint32_t a0[32], a1[32];
+            tmem_ld32_issue(tl + T_ACC2, a0);
+            tmem_ld32_issue(tl + T_ACC2 + 32, a1);
+            tmem_ld_wait();
+            float s = dot32(a0, 0, 0.f);
+            s = dot32(a1, 32, s);
+            tmem_ld32_issue(tl + T_ACC2 + 64, a0);
+            tmem_ld32_issue(tl + T_ACC2 + 96, a1);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(BAR(B_ACC2E));            // the next tile's layer 1 may overwrite the accumulator
+            if (tid == 320) TL(133);
+            s = dot32(a0, 64, s);
+            s = dot32(a1, 96, s);
+            if (pi < q.N) {
+#pragma unroll
+                for (int j = 0; j < 15; ++j) s = fmaf(sw3[128 + j], xf[j * TC_M + r], s);    // skip connection; rows >= c0 are zero
+                s += sb3[0];
+                q.out[pi] = xf[15 * TC_M + r] * s;            // in_cube flag
+            }
+            if (tid == 320) TL(134);
         }
     }
 
@@ -467,8 +561,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_query_mlp_tc(QueryParams q, c
 template <int MODE>
 int launch_mlp_tc_t(const QueryParams &q, const void *blob, cudaStream_t stream) {
     static bool attr_set[ICON_MAX_DEVICES] = {};
-    if (device_needs_setup(attr_set))
+    if (device_needs_setup(attr_set)) {
         ICON_CUDA(cudaFuncSetAttribute(k_query_mlp_tc<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    }
+
     const int sms = device_sm_count();
     const int64_t ntiles = (q.N + TC_M - 1) / TC_M;
     const unsigned grid = (unsigned)(ntiles < sms ? ntiles : sms);
@@ -476,6 +572,14 @@ int launch_mlp_tc_t(const QueryParams &q, const void *blob, cudaStream_t stream)
     ICON_LAUNCHED();
     return ICON_OK;
 }
+
+#ifdef ICON_MLP_TIMELINE
+}  // namespace icon
+extern "C" int icon_debug_mlp_timeline(long long *h_out) {
+    return cudaMemcpyFromSymbol(h_out, icon::g_tl, sizeof(long long) * 256) == cudaSuccess ? 0 : 1;
+}
+namespace icon {
+#endif
 
 int launch_mlp_tc(int mode, const QueryParams &q, const void *blob, cudaStream_t stream) {
     switch (mode) {
