@@ -27,7 +27,10 @@
 //               the accumulator has been read).
 // Layer-0 chunks are issued two ahead of the layer-1 chunk that consumes them, so the tensor pipe
 // always has queued work while the workers convert.  TMEM map (512 columns):
-//   [0,256) layer-1 accumulator (later [0,128) layer-2 accumulator)
+//   [0,256) layer-1 accumulator (later [0,128) layer-2 accumulator and, once the workers have converted columns
+//           128..191, [128,192) = layer-0 chunk 0 of the NEXT tile (its chunk 1 goes to [384,448) once layer-2 K-chunks
+//           0 and 1 are done), so that its layer 1 can start as soon as the epilogue warps have read this tile's
+//           layer-2 accumulator)
 //   [256,384) 2 x (hi 32 | lo 32) A-operand chunks of layer 1   } later: layer-1 activations
 //   [384,512) 2 x 64 layer-0 accumulator chunks                 } hi [256,384), lo [384,512)
 // Where the cycles of a tile go was measured with tools/mlp_timeline.py (profiles/r2_summary.md).
@@ -39,7 +42,7 @@
 
 namespace icon {
 
-constexpr int TC_THREADS = 448;      // 1 producer + 1 MMA + 8 worker + 4 gather warps
+constexpr int TC_THREADS = 576;      // 1 producer + 1 MMA + 8 worker + 4 gather/epilogue + 4 epilogue warps
 constexpr int TC_M = 128;
 
 // byte offsets inside the packed tensor-core weight blob (host: icon_b200/ops.py pack_mlp_tc)
@@ -60,7 +63,8 @@ constexpr int SM_X0L = SM_X0H + 8192;             // 2 x 4096
 constexpr int SM_X0F = SM_X0L + 8192;             // 2 x [16][128] fp32
 constexpr int SM_F32 = SM_X0F + 2 * 8192;         // biases etc.
 constexpr int SM_W2T = (SM_F32 + TCB_F32_FLOATS * 4 + 127) / 128 * 128;   // 8192: x0 tail of layer 2 (hi 4096 | lo 4096), resident
-constexpr int SM_BAR = SM_W2T + 8192;             // 24 mbarriers
+constexpr int SM_PART = SM_W2T + 8192;            // 2 x [128] fp32 layer-3 partials (columns 64..127)
+constexpr int SM_BAR = SM_PART + 1024;            // 24 mbarriers
 constexpr int SM_MISC = SM_BAR + 24 * 8;
 constexpr int SM_TOTAL = SM_MISC + 64;
 constexpr int TC_SMEM_BYTES = SM_TOTAL + 1024;    // slack for manual 1024-B alignment
@@ -70,6 +74,7 @@ enum { B_WFULL0 = 0, B_WFULL1, B_WEMPTY0, B_WEMPTY1, B_X0R0, B_X0R1, B_ACC2E, B_
 
 // TMEM columns
 constexpr uint32_t T_ACC1 = 0, T_A0 = 256, T_ACC0 = 384, T_ACT1H = 256, T_ACT1L = 384, T_ACC2 = 0;
+constexpr uint32_t T_ACC0E = 128;     // layer-0 chunk 0 of the NEXT tile, computed while this tile is in layer 2
 
 // ---------------------------------------------------------------- PTX helpers
 __device__ __forceinline__ uint32_t s32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -205,6 +210,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_query_mlp_tc(QueryParams q, c
     float *x0f = reinterpret_cast<float *>(sm + SM_X0F);
     const float *sf32 = reinterpret_cast<const float *>(sm + SM_F32);
     const float *sb0 = sf32, *sb1 = sf32 + 512, *sb2 = sf32 + 768, *sw3 = sf32 + 896, *sb3 = sf32 + 1040;
+    float *spart = reinterpret_cast<float *>(sm + SM_PART);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sm + SM_MISC);
     const uint32_t bar0 = base + SM_BAR;
     auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
@@ -217,7 +223,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_query_mlp_tc(QueryParams q, c
         mbar_init(BAR(B_WFULL0), 1); mbar_init(BAR(B_WFULL1), 1);
         mbar_init(BAR(B_WEMPTY0), 1); mbar_init(BAR(B_WEMPTY1), 1);
         mbar_init(BAR(B_X0R0), 128); mbar_init(BAR(B_X0R1), 128);      // gather warps -> MMA
-        mbar_init(BAR(B_ACC2E), 128); mbar_init(BAR(B_SPARE), 1);     // epilogue: layer-2 accumulator has been read
+        mbar_init(BAR(B_ACC2E), 256); mbar_init(BAR(B_SPARE), 1);     // epilogue: layer-2 accumulator has been read
         mbar_init(BAR(B_ACC0F0), 1); mbar_init(BAR(B_ACC0F1), 1);
         mbar_init(BAR(B_A0F0), 256); mbar_init(BAR(B_A0F1), 256);
         mbar_init(BAR(B_A0E0), 1); mbar_init(BAR(B_A0E1), 1);
@@ -263,30 +269,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_query_mlp_tc(QueryParams q, c
             const uint64_t dx0h0 = desc_nosw(base + SM_X0H, 2048, 128), dx0l0 = desc_nosw(base + SM_X0L, 2048, 128);
             const uint64_t dw0h = desc_nosw(base + SM_W0, 8192, 128), dw0l = desc_nosw(base + SM_W0 + 16384, 8192, 128);
             uint32_t ph_x0 = 0, ph_a0f = 0, ph_act1 = 0, cnt = 0, tcount = 0;     // per-buffer phase bits
-            uint64_t dx0h = dx0h0, dx0l = dx0l0;
             mbar_wait(BAR(B_W0RDY), 0);
-            auto L0 = [&](int j) {
-                const uint32_t d = tm + T_ACC0 + 64u * (uint32_t)(j & 1);
+            auto L0 = [&](int j, uint32_t xb, uint32_t dcol) {          // layer-0 chunk j of the tile whose x0 is in buffer xb
+                const uint32_t d = tm + dcol;
+                const uint64_t ah = dx0h0 + (uint64_t)(xb * 256), al = dx0l0 + (uint64_t)(xb * 256);     // 4096 B = 256 units
                 const uint64_t o = (uint64_t)(j * 64);              // 64 rows = 8 groups x 128 B = 1024 B -> 64 units
                 if (elect_one()) {
-                    mma_ss(d, dx0h, dw0h + o, ID64, 0);
-                    mma_ss(d, dx0h, dw0l + o, ID64, 1);
-                    mma_ss(d, dx0l, dw0h + o, ID64, 1);
+                    mma_ss(d, ah, dw0h + o, ID64, 0);
+                    mma_ss(d, ah, dw0l + o, ID64, 1);
+                    mma_ss(d, al, dw0h + o, ID64, 1);
                     tc_commit(BAR(B_ACC0F0 + (j & 1)));
                 }
                 __syncwarp();
             };
-            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
-                const uint32_t xb = tcount & 1;
-                dx0h = dx0h0 + (uint64_t)(xb * 4096 / 16);
-                dx0l = dx0l0 + (uint64_t)(xb * 4096 / 16);
-                if (lane == 0) TL(0);
+            auto L0_early = [&](uint32_t xb) {      // chunk 0 -> [128,192) (dead layer-1 columns), chunk 1 -> [384,448) (ACT1L of finished K-chunks)
                 mbar_wait(BAR(B_X0R0 + xb), (ph_x0 >> xb) & 1); ph_x0 ^= 1u << xb;
                 tc_fence_after();
-                if (lane == 0) TL(1);
-                L0(0);
-                L0(1);
-                if (lane == 0) TL(2);
+                L0(0, xb, T_ACC0E);
+                L0(1, xb, T_ACC0);
+            };
+            if ((int64_t)blockIdx.x < ntiles) L0_early(0);
+            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+                const uint32_t xb = tcount & 1;
+                if (lane == 0) TL(0);
                 uint32_t s_cur = 0, s_nxt = 0;
                 auto wait_a0 = [&](int j) {
                     const int b = j & 1;
@@ -312,7 +317,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_query_mlp_tc(QueryParams q, c
                         }
                         if (ks1 == 4) {
                             tc_commit(BAR(B_WEMPTY0 + s_cur));
-                            tc_commit(BAR(B_A0E0 + b));
+                            if (j < 6) tc_commit(BAR(B_A0E0 + b));      // chunks 6, 7: released after layer 2 (their columns become ACT1H)
                         }
                     }
                     __syncwarp();
@@ -328,21 +333,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_query_mlp_tc(QueryParams q, c
                             mma_ts(tm + T_ACC2, ah, bl + 2 * ks, ID128, 1);
                             mma_ts(tm + T_ACC2, al, bh + 2 * ks, ID128, 1);
                         }
-                        if (ks1 == 4 && (c & 1)) tc_commit(BAR(B_WEMPTY0 + s_cur));
+                        if (ks1 == 4 && (c & 1)) {
+                            tc_commit(BAR(B_WEMPTY0 + s_cur));
+                            tc_commit(BAR(B_A0E0 + (c >> 1)));          // ACT1H chunks (c-1, c) = A-operand buffer c/2 of the next tile
+                        }
                     }
                     __syncwarp();
                 };
+                // Layer 1 overwrites [0,256): the early layer-0 chunk 0 must have been converted, and the epilogue warps
+                // must have read the previous tile's layer-2 accumulator.
                 wait_a0(0); wait_w(3); s_cur = s_nxt;
-                if (tcount) {                                  // the epilogue warps have read the previous tile's layer-2 accumulator
+                if (tcount) {
                     mbar_wait(BAR(B_ACC2E), (tcount - 1) & 1);
                     tc_fence_after();
                 }
+                if (lane == 0) TL(1);
 #pragma unroll 1
                 for (int j = 0; j < 8; ++j) {
                     l1_ks(j, 0, 3);
-                    if (j < 7) { wait_a0(j + 1); wait_w(3 + 2 * (j + 1)); }      // chunk j+1, while chunk j still has MMAs to issue
+                    if (j < 7) {                                    // chunk j+1, while chunk j still has MMAs to issue
+                        wait_a0(j + 1);
+                        wait_w(3 + 2 * (j + 1));
+                    }
                     l1_ks(j, 3, 4);
-                    if (j + 2 < 8) L0(j + 2);
+                    if (j + 2 < 8) L0(j + 2, xb, T_ACC0 + 64u * (uint32_t)(j & 1));
                     s_cur = s_nxt;
                     if (lane == 0) TL(4 + 2 * j);
                 }
@@ -360,15 +374,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_query_mlp_tc(QueryParams q, c
                 l2_ks(0, 0, 3); wait_act1(1); l2_ks(0, 3, 4);
                 l2_ks(1, 0, 3); wait_act1(2); wait_w(22); l2_ks(1, 3, 4);
                 s_cur = s_nxt;
-                l2_ks(2, 0, 3); wait_act1(3); l2_ks(2, 3, 4);
+                // layer-1 columns 128..191 are converted (ACT1 chunk 2) and layer-2 K-chunks 0, 1 are ahead in the pipe:
+                if (tile + gridDim.x < ntiles) L0_early(xb ^ 1);
+                if (lane == 0) TL(2);
+                l2_ks(2, 0, 3); wait_act1(3);
+                l2_ks(2, 3, 4);
                 l2_ks(3, 0, 4);
                 ph_act1 ^= 1;
                 {
+                    const uint64_t ah = dx0h0 + (uint64_t)(xb * 256), al = dx0l0 + (uint64_t)(xb * 256);
                     const uint64_t th = desc_nosw(base + SM_W2T, 2048, 128), tl = desc_nosw(base + SM_W2T + 4096, 2048, 128);
                     if (elect_one()) {
-                        mma_ss(tm + T_ACC2, dx0h, th, ID128, 1);
-                        mma_ss(tm + T_ACC2, dx0h, tl, ID128, 1);
-                        mma_ss(tm + T_ACC2, dx0l, th, ID128, 1);
+                        mma_ss(tm + T_ACC2, ah, th, ID128, 1);
+                        mma_ss(tm + T_ACC2, ah, tl, ID128, 1);
+                        mma_ss(tm + T_ACC2, al, th, ID128, 1);
                         tc_commit(BAR(B_ACC2));
                     }
                     __syncwarp();
@@ -393,7 +412,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_query_mlp_tc(QueryParams q, c
                 tc_fence_after();
                 if (tid == 64) TL(64 + 4 * j);
                 uint32_t acc[32], hi[16], lo[16];
-                tmem_ld32(tl + T_ACC0 + 64u * b + 32u * h, acc);
+                tmem_ld32(tl + (j == 0 ? T_ACC0E : j == 1 ? T_ACC0 : T_ACC0 + 64u * b) + 32u * h, acc);
                 if (tid == 64) TL(65 + 4 * j);
                 act_split32(acc, sb0 + 64 * j + 32 * h, hi, lo);
                 if (tid == 64) TL(66 + 4 * j);
@@ -423,7 +442,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_query_mlp_tc(QueryParams q, c
                 if (tid == 64) TL(101 + t);
             }
         }
-    } else {
+    } else if (warp < 14) {
         // ======================================================== gather + epilogue warps (4 warps, one row per thread)
         const int q4 = warp & 3;
         const int r = q4 * 32 + lane;             // row of the tile = TMEM lane this warp may touch
@@ -526,26 +545,55 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_query_mlp_tc(QueryParams q, c
             tc_fence_after();
             if (tid == 320) TL(132);
             uint32_t a0[32], a1[32];
-            tmem_ld32_issue(tl + T_ACC2, a0);
+            tmem_ld32_issue(tl + T_ACC2, a0);                 // columns 0..63 here, 64..127 in warps 14-17
             tmem_ld32_issue(tl + T_ACC2 + 32, a1);
-            tmem_ld_wait();
-            float s = dot32(a0, 0, 0.f);
-            s = dot32(a1, 32, s);
-            tmem_ld32_issue(tl + T_ACC2 + 64, a0);
-            tmem_ld32_issue(tl + T_ACC2 + 96, a1);
             tmem_ld_wait();
             tc_fence_before();
             mbar_arrive(BAR(B_ACC2E));            // the next tile's layer 1 may overwrite the accumulator
             if (tid == 320) TL(133);
-            s = dot32(a0, 64, s);
-            s = dot32(a1, 96, s);
+            float s = dot32(a0, 0, 0.f);
+            s = dot32(a1, 32, s);
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             if (pi < q.N) {
+                s += spart[xb * TC_M + r];
 #pragma unroll
                 for (int j = 0; j < 15; ++j) s = fmaf(sw3[128 + j], xf[j * TC_M + r], s);    // skip connection; rows >= c0 are zero
                 s += sb3[0];
                 q.out[pi] = xf[15 * TC_M + r] * s;            // in_cube flag
             }
             if (tid == 320) TL(134);
+        }
+    } else {
+        // ======================================================== epilogue warps 14-17: layer-3 partial over columns 64..127
+        const int q4 = warp & 3;
+        const int r = q4 * 32 + lane;
+        const uint32_t tl = tmem + ((uint32_t)(q4 * 32) << 16);
+        uint32_t ph_acc2 = 0, tcount = 0;
+        mbar_wait(BAR(B_W0RDY), 0);
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+            mbar_wait(BAR(B_ACC2), ph_acc2); ph_acc2 ^= 1;
+            tc_fence_after();
+            uint32_t a0[32], a1[32];
+            tmem_ld32_issue(tl + T_ACC2 + 64, a0);
+            tmem_ld32_issue(tl + T_ACC2 + 96, a1);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(BAR(B_ACC2E));
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                float v = __uint_as_float(a0[i]) + sb2[64 + i];
+                v = fmaxf(v, 0.01f * v);
+                s = fmaf(sw3[64 + i], v, s);
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                float v = __uint_as_float(a1[i]) + sb2[96 + i];
+                v = fmaxf(v, 0.01f * v);
+                s = fmaf(sw3[96 + i], v, s);
+            }
+            spart[(tcount & 1) * TC_M + r] = s;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
         }
     }
 
