@@ -27,10 +27,7 @@
 //               the accumulator has been read).
 // Layer-0 chunks are issued two ahead of the layer-1 chunk that consumes them, so the tensor pipe
 // always has queued work while the workers convert.  TMEM map (512 columns):
-//   [0,256) layer-1 accumulator (later [0,128) layer-2 accumulator and, once the workers have converted columns
-//           128..191, [128,192) = layer-0 chunk 0 of the NEXT tile (its chunk 1 goes to [384,448) once layer-2 K-chunks
-//           0 and 1 are done), so that its layer 1 can start as soon as the epilogue warps have read this tile's
-//           layer-2 accumulator)
+//   [0,256) layer-1 accumulator (later [0,128) layer-2 accumulator)
 //   [256,384) 2 x (hi 32 | lo 32) A-operand chunks of layer 1   } later: layer-1 activations
 //   [384,512) 2 x 64 layer-0 accumulator chunks                 } hi [256,384), lo [384,512)
 // Where the cycles of a tile go was measured with tools/mlp_timeline.py (profiles/r2_summary.md).
@@ -74,7 +71,6 @@ enum { B_WFULL0 = 0, B_WFULL1, B_WEMPTY0, B_WEMPTY1, B_X0R0, B_X0R1, B_ACC2E, B_
 
 // TMEM columns
 constexpr uint32_t T_ACC1 = 0, T_A0 = 256, T_ACC0 = 384, T_ACT1H = 256, T_ACT1L = 384, T_ACC2 = 0;
-constexpr uint32_t T_ACC0E = 128;     // layer-0 chunk 0 of the NEXT tile, computed while this tile is in layer 2
 
 // ---------------------------------------------------------------- PTX helpers
 __device__ __forceinline__ uint32_t s32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -282,16 +278,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_query_mlp_tc(QueryParams q, c
                 }
                 __syncwarp();
             };
-            auto L0_early = [&](uint32_t xb) {      // chunk 0 -> [128,192) (dead layer-1 columns), chunk 1 -> [384,448) (ACT1L of finished K-chunks)
-                mbar_wait(BAR(B_X0R0 + xb), (ph_x0 >> xb) & 1); ph_x0 ^= 1u << xb;
-                tc_fence_after();
-                L0(0, xb, T_ACC0E);
-                L0(1, xb, T_ACC0);
-            };
-            if ((int64_t)blockIdx.x < ntiles) L0_early(0);
             for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
                 const uint32_t xb = tcount & 1;
                 if (lane == 0) TL(0);
+                mbar_wait(BAR(B_X0R0 + xb), (ph_x0 >> xb) & 1); ph_x0 ^= 1u << xb;
+                tc_fence_after();
+                L0(0, xb, T_ACC0);                  // [384,512) was ACT1L of the previous tile: its layer-2 MMAs are ahead in the pipe
+                L0(1, xb, T_ACC0 + 64);
                 uint32_t s_cur = 0, s_nxt = 0;
                 auto wait_a0 = [&](int j) {
                     const int b = j & 1;
@@ -317,7 +310,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_query_mlp_tc(QueryParams q, c
                         }
                         if (ks1 == 4) {
                             tc_commit(BAR(B_WEMPTY0 + s_cur));
-                            if (j < 6) tc_commit(BAR(B_A0E0 + b));      // chunks 6, 7: released after layer 2 (their columns become ACT1H)
+                            tc_commit(BAR(B_A0E0 + b));
                         }
                     }
                     __syncwarp();
@@ -333,15 +326,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_query_mlp_tc(QueryParams q, c
                             mma_ts(tm + T_ACC2, ah, bl + 2 * ks, ID128, 1);
                             mma_ts(tm + T_ACC2, al, bh + 2 * ks, ID128, 1);
                         }
-                        if (ks1 == 4 && (c & 1)) {
-                            tc_commit(BAR(B_WEMPTY0 + s_cur));
-                            tc_commit(BAR(B_A0E0 + (c >> 1)));          // ACT1H chunks (c-1, c) = A-operand buffer c/2 of the next tile
-                        }
+                        if (ks1 == 4 && (c & 1)) tc_commit(BAR(B_WEMPTY0 + s_cur));
                     }
                     __syncwarp();
                 };
-                // Layer 1 overwrites [0,256): the early layer-0 chunk 0 must have been converted, and the epilogue warps
-                // must have read the previous tile's layer-2 accumulator.
+                // Layer 1 overwrites [0,256): the epilogue warps must have read the previous tile's layer-2 accumulator.
                 wait_a0(0); wait_w(3); s_cur = s_nxt;
                 if (tcount) {
                     mbar_wait(BAR(B_ACC2E), (tcount - 1) & 1);
@@ -374,11 +363,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_query_mlp_tc(QueryParams q, c
                 l2_ks(0, 0, 3); wait_act1(1); l2_ks(0, 3, 4);
                 l2_ks(1, 0, 3); wait_act1(2); wait_w(22); l2_ks(1, 3, 4);
                 s_cur = s_nxt;
-                // layer-1 columns 128..191 are converted (ACT1 chunk 2) and layer-2 K-chunks 0, 1 are ahead in the pipe:
-                if (tile + gridDim.x < ntiles) L0_early(xb ^ 1);
-                if (lane == 0) TL(2);
-                l2_ks(2, 0, 3); wait_act1(3);
-                l2_ks(2, 3, 4);
+                l2_ks(2, 0, 3); wait_act1(3); l2_ks(2, 3, 4);
                 l2_ks(3, 0, 4);
                 ph_act1 ^= 1;
                 {
@@ -412,7 +397,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_query_mlp_tc(QueryParams q, c
                 tc_fence_after();
                 if (tid == 64) TL(64 + 4 * j);
                 uint32_t acc[32], hi[16], lo[16];
-                tmem_ld32(tl + (j == 0 ? T_ACC0E : j == 1 ? T_ACC0 : T_ACC0 + 64u * b) + 32u * h, acc);
+                tmem_ld32(tl + T_ACC0 + 64u * b + 32u * h, acc);
                 if (tid == 64) TL(65 + 4 * j);
                 act_split32(acc, sb0 + 64 * j + 32 * h, hi, lo);
                 if (tid == 64) TL(66 + 4 * j);

@@ -24,7 +24,7 @@ buf = (ctypes.c_longlong * 256)()
 assert lib.icon_debug_mlp_timeline(buf) == 0
 t = list(buf)
 t0 = t[0]
-names = {0: "mma tile start", 1: "mma x0 ready", 2: "mma L0(0,1) issued", 19: "mma ACC1 committed", 25: "mma ACC2 committed",
+names = {0: "mma tile start", 1: "mma ACC2E seen (layer 1 may start)", 19: "mma ACC1 committed", 25: "mma ACC2 committed",
          20: "mma W2(0,1) seen", 22: "mma W2(2,3) seen", 100: "wrk ACC1 seen",
          128: "epi iteration start", 131: "epi next tile's x0 published", 132: "epi ACC2 seen", 133: "epi ACC2 read (ACC2E arrived)",
          134: "epi tile stored"}
