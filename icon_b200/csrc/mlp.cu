@@ -314,6 +314,10 @@ static int launch_any(const QueryParams &q, const void *tc, cudaStream_t stream)
                       "pass it or select the FP32 kernel with icon_set_mlp_impl(0)");
             return ICON_EINVAL;
         }
+        if (q.c0 > 15) {    // x0 column 15 is the constant 1 that carries the folded biases
+            set_error("icon_query / icon_mlp_only: the tcgen05 MLP takes c0 <= 15 input channels (got %d)", q.c0);
+            return ICON_EINVAL;
+        }
         return launch_mlp_tc(MODE, q, tc, stream);
     }
     return launch_mlp<MODE>(q, stream);

@@ -173,12 +173,13 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t &hi, uint32_t 
     lo = *reinterpret_cast<uint32_t *>(&l);
 }
 
-// bias + LeakyReLU + split of 32 accumulator values -> 16 hi words + 16 lo words
+// [bias +] LeakyReLU + split of 32 accumulator values -> 16 hi words + 16 lo words (bias == nullptr: already in the
+// accumulator, folded into the MMA through the constant-1 input column)
 __device__ __forceinline__ void act_split32(const uint32_t (&acc)[32], const float *__restrict__ bias, uint32_t (&hi)[16],
                                             uint32_t (&lo)[16]) {
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
-        float4 b = *reinterpret_cast<const float4 *>(bias + i);
+        float4 b = bias ? *reinterpret_cast<const float4 *>(bias + i) : make_float4(0.f, 0.f, 0.f, 0.f);
         float v0 = __uint_as_float(acc[i]) + b.x, v1 = __uint_as_float(acc[i + 1]) + b.y;
         float v2 = __uint_as_float(acc[i + 2]) + b.z, v3 = __uint_as_float(acc[i + 3]) + b.w;
         v0 = fmaxf(v0, 0.01f * v0); v1 = fmaxf(v1, 0.01f * v1);
@@ -399,7 +400,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_query_mlp_tc(QueryParams q, c
                 uint32_t acc[32], hi[16], lo[16];
                 tmem_ld32(tl + T_ACC0 + 64u * b + 32u * h, acc);
                 if (tid == 64) TL(65 + 4 * j);
-                act_split32(acc, sb0 + 64 * j + 32 * h, hi, lo);
+                act_split32(acc, nullptr, hi, lo);               // b0 rides on x0 column 15 = 1
                 if (tid == 64) TL(66 + 4 * j);
                 mbar_wait(BAR(B_A0E0 + b), ((ph_a0e >> b) & 1) ^ 1); ph_a0e ^= 1u << b;
                 tc_fence_after();
@@ -495,7 +496,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_query_mlp_tc(QueryParams q, c
             for (int j = 0; j < 15; ++j) xf[j * TC_M + r] = f[j];
             xf[15 * TC_M + r] = in_cube;                      // c0 <= 13: row 15 is spare
 #pragma unroll
-            for (int i = 0; i < 8; ++i) split2(f[2 * i], f[2 * i + 1], hi[i], lo[i]);
+            for (int i = 0; i < 7; ++i) split2(f[2 * i], f[2 * i + 1], hi[i], lo[i]);
+            split2(f[14], 1.f, hi[7], lo[7]);                 // column 15 = 1: carries b0 (layer 0) and b2 (x0 tail of layer 2)
             const int off = (int)xb * 4096 + (r >> 3) * 128 + (r & 7) * 16;
             *reinterpret_cast<uint4 *>(sm + SM_X0H + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
             *reinterpret_cast<uint4 *>(sm + SM_X0H + off + 2048) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
@@ -504,12 +506,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_query_mlp_tc(QueryParams q, c
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(BAR(B_X0R0 + xb));
         };
-        // 32 columns of layer 3: LeakyReLU(acc + b2) . w3
+        // 32 columns of layer 3: LeakyReLU(acc) . w3 (b2 is already in the accumulator)
         auto dot32 = [&](const uint32_t (&acc)[32], int col, float s) {
-            const float *bb = sb2 + col, *ww = sw3 + col;
+            const float *ww = sw3 + col;
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-                float v = __uint_as_float(acc[i]) + bb[i];
+                float v = __uint_as_float(acc[i]);
                 v = fmaxf(v, 0.01f * v);
                 s = fmaf(ww[i], v, s);
             }
@@ -567,13 +569,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_query_mlp_tc(QueryParams q, c
             float s = 0.f;
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-                float v = __uint_as_float(a0[i]) + sb2[64 + i];
+                float v = __uint_as_float(a0[i]);
                 v = fmaxf(v, 0.01f * v);
                 s = fmaf(sw3[64 + i], v, s);
             }
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-                float v = __uint_as_float(a1[i]) + sb2[96 + i];
+                float v = __uint_as_float(a1[i]);
                 v = fmaxf(v, 0.01f * v);
                 s = fmaf(sw3[96 + i], v, s);
             }

@@ -91,9 +91,9 @@ def _fold_mlp(sd, c0, prefix=""):
         dims.append(tuple(sd[prefix + f"filters.{l}.weight"].shape[:2]))
         l += 1
     expect = [(512, c0), (256, 512), (128, 256 + c0), (1, 128 + c0)]
-    if dims != expect or c0 > 16:
+    if dims != expect or c0 > 15:      # input column 15 of the tensor-core tiles carries the constant 1 that folds b0 / b2 in
         raise NotImplementedError(
-            f"fused MLP kernel supports mlp_dim [c0<=16,512,256,128,1] with res_layers [2,3,4]; got {dims}")
+            f"fused MLP kernel supports mlp_dim [c0<=15,512,256,128,1] with res_layers [2,3,4]; got {dims}")
     Ws, bs = [], []
     for l in range(4):
         W = g(f"filters.{l}.weight")[:, :, 0]
@@ -150,12 +150,16 @@ def pack_mlp(sd, c0, prefix="", device=None):
                      W2.t().contiguous().reshape(-1), b2, W3, b3]).float()
     assert f32.numel() == MLP_PACKED_FLOATS
     blob = bytearray()
-    h, l = _hi_lo(W0)
+    # tensor-core tiles: the kernel feeds x0 column 15 = 1, so row 15 of W0 and of the x0 tail of W2 carry the biases
+    # b0 / b2 (hi + lo fp16 like every weight: 22 significant bits); b1 stays an fp32 add in the conversion step
+    W0b = W0.clone(); W0b[:, 15] = b0
+    W2b = W2.clone(); W2b[:, 256 + 15] = b2
+    h, l = _hi_lo(W0b)
     blob += _img_nosw(h) + _img_nosw(l)
     h, l = _hi_lo(W1)
     for j in range(8):
         blob += _img_sw128(h[:, 64 * j:64 * j + 64]) + _img_sw128(l[:, 64 * j:64 * j + 64])
-    h, l = _hi_lo(W2)
+    h, l = _hi_lo(W2b)
     for j in range(4):
         blob += _img_sw128(h[:, 64 * j:64 * j + 64]) + _img_sw128(l[:, 64 * j:64 * j + 64])
     blob += _img_nosw(np.ascontiguousarray(h[:, 256:272])) + _img_nosw(np.ascontiguousarray(l[:, 256:272]))

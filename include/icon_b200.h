@@ -73,10 +73,11 @@ int icon_smpl_prepare(const float *verts, const int64_t *faces, const float *cma
 #define ICON_MLP_PACKED_FLOATS (16 * 512 + 512 + 512 * 256 + 256 + 272 * 128 + 128 + 144 + 1)
 /* Tensor-core form of the same folded weights (host: icon_b200/ops.py pack_mlp): every matrix
  * split W = hi + lo in fp16 and stored as ready-to-use K-major UMMA tiles (bytes):
- *   W0  hi 16384 | lo 16384    512 rows x 16 k, no swizzle (LBO 8192, SBO 128)
+ *   W0  hi 16384 | lo 16384    512 rows x 16 k, no swizzle (LBO 8192, SBO 128); k = 15 holds b0: the kernel feeds
+ *                              x0 column 15 = 1, so the tensor-core path takes c0 <= 15
  *   W1  8 x (hi 32768 | lo 32768)   256 rows x 64 k per chunk, SWIZZLE_128B
  *   W2  4 x (hi 16384 | lo 16384)   128 rows x 64 k per chunk, SWIZZLE_128B
- *   W2t hi 4096 | lo 4096      128 rows x 16 k (the skip-concat x0 columns), no swizzle
+ *   W2t hi 4096 | lo 4096      128 rows x 16 k (the skip-concat x0 columns), no swizzle; k = 15 holds b2
  *   f32 b0[512] b1[256] b2[128] w3[144] b3[1] pad[3] */
 #define ICON_MLP_TC_BYTES (32768 + 8 * 65536 + 4 * 32768 + 8192 + (512 + 256 + 128 + 144 + 4) * 4)
 /* 0 = FP32 FMA kernel (mlp.cu), 1 = tcgen05 fp16x3 kernel (mlp_tc.cu, default when mlp_tc != NULL) */
