@@ -84,6 +84,16 @@ class ClockSampler:
         self.index = index
         self.rows = []
         self.proc = None
+        self.first = 0
+
+    def mark(self, wait_s=3.0):
+        """Call right before the timed region: nvidia-smi was started long before (its start-up takes driver locks and
+        can stall kernel launches for tens of ms -- seen as a 2x outlier of the resident figure when it was spawned right
+        here); wait until it is in its steady 25 ms polling loop and count only the rows from now on."""
+        t0 = time.time()
+        while self.proc is not None and not self.rows and time.time() - t0 < wait_s:
+            time.sleep(0.01)
+        self.first = len(self.rows)
 
     def start(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -108,7 +118,7 @@ class ClockSampler:
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in self.rows[self.first:]:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
                 continue
@@ -553,14 +563,16 @@ def main():
             out = query(im, pts_dev)
         return out
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                       # before the warm-up: see ClockSampler.mark
     for _ in range(args.warmup):
         step_resident()
     barrier()
 
     # ---- timed region 1: inputs resident in HBM
-    sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.mark()
     l0 = _C.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()

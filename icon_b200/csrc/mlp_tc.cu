@@ -41,6 +41,7 @@ namespace icon {
 
 constexpr int TC_THREADS = 576;      // 1 producer + 1 MMA + 8 worker + 4 gather/epilogue + 4 epilogue warps
 constexpr int TC_M = 128;
+constexpr unsigned EPI_YIELD_NS = 1200;  // epilogue warps sleep this long after reading the layer-2 accumulator (measured: tools/mlp_timeline.py)
 
 // byte offsets inside the packed tensor-core weight blob (host: icon_b200/ops.py pack_mlp_tc)
 constexpr int TCB_W0 = 0;                         // hi 16384 | lo 16384, no swizzle, LBO 8192, SBO 128
@@ -531,6 +532,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_query_mlp_tc(QueryParams q, c
             mbar_wait(BAR(B_ACC2), ph_acc2); ph_acc2 ^= 1;
             tc_fence_after();
             if (tid == 320) TL(132);
+            if (tid == 416) TL(140);
             uint32_t a0[32], a1[32];
             tmem_ld32_issue(tl + T_ACC2, a0);                 // columns 0..63 here, 64..127 in warps 14-17
             tmem_ld32_issue(tl + T_ACC2 + 32, a1);
@@ -538,6 +540,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_query_mlp_tc(QueryParams q, c
             tc_fence_before();
             mbar_arrive(BAR(B_ACC2E));            // the next tile's layer 1 may overwrite the accumulator
             if (tid == 320) TL(133);
+            if (tid == 416) TL(141);
+            __nanosleep(EPI_YIELD_NS);            // the workers are converting the next tile's first chunk (critical path): stay out of their issue slots
             float s = dot32(a0, 0, 0.f);
             s = dot32(a1, 32, s);
             asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -560,12 +564,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_query_mlp_tc(QueryParams q, c
         for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
             mbar_wait(BAR(B_ACC2), ph_acc2); ph_acc2 ^= 1;
             tc_fence_after();
+            if (tid == 544) TL(142);
             uint32_t a0[32], a1[32];
             tmem_ld32_issue(tl + T_ACC2 + 64, a0);
             tmem_ld32_issue(tl + T_ACC2 + 96, a1);
             tmem_ld_wait();
             tc_fence_before();
             mbar_arrive(BAR(B_ACC2E));
+            if (tid == 544) TL(143);
+            __nanosleep(EPI_YIELD_NS);
             float s = 0.f;
 #pragma unroll
             for (int i = 0; i < 32; ++i) {

@@ -27,7 +27,8 @@ t0 = t[0]
 names = {0: "mma tile start", 1: "mma ACC2E seen (layer 1 may start)", 19: "mma ACC1 committed", 25: "mma ACC2 committed",
          20: "mma W2(0,1) seen", 22: "mma W2(2,3) seen", 100: "wrk ACC1 seen",
          128: "epi iteration start", 131: "epi next tile's x0 published", 132: "epi ACC2 seen", 133: "epi ACC2 read (ACC2E arrived)",
-         134: "epi tile stored"}
+         134: "epi tile stored", 140: "epi warp 13 ACC2 seen", 141: "epi warp 13 ACC2E arrived", 142: "epi warp 17 ACC2 seen",
+         143: "epi warp 17 ACC2E arrived"}
 for j in range(8):
     names[32 + j] = f"mma A0F({j}) seen"; names[3 + 2 * j] = f"mma W({j}) seen"; names[4 + 2 * j] = f"mma L1({j}) issued"
     names[64 + 4 * j] = f"wrk ACC0F({j}) seen"; names[65 + 4 * j] = f"wrk ld({j}) done"; names[66 + 4 * j] = f"wrk math({j}) done"
