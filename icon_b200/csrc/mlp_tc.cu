@@ -333,11 +333,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_query_mlp_tc(QueryParams q, c
                     __syncwarp();
                 };
                 // Layer 1 overwrites [0,256): the epilogue warps must have read the previous tile's layer-2 accumulator.
-                wait_a0(0); wait_w(3); s_cur = s_nxt;
-                if (tcount) {
-                    mbar_wait(BAR(B_ACC2E), (tcount - 1) & 1);
-                    tc_fence_after();
-                }
+                // The three waits are taken in the order the barriers complete (weights long ago, accumulator read ~0.9 k
+                // clocks into the tile, first converted chunk ~1.3 k): each costs a few hundred clocks of this warp's thin
+                // share of the scheduler even when already complete, and only the last one should be exposed.
+                wait_w(3); s_cur = s_nxt;
+                if (tcount) mbar_wait(BAR(B_ACC2E), (tcount - 1) & 1);
+                wait_a0(0);
+                tc_fence_after();
                 if (lane == 0) TL(1);
 #pragma unroll 1
                 for (int j = 0; j < 8; ++j) {
