@@ -1,11 +1,19 @@
 """N>1 plumbing on CPU: world_size-2 gloo (the GPU path uses the same functions over NCCL)."""
 import os
+import socket
 
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from icon_b200 import dist as D
+
+
+def _free_port():
+    """A port the OS says is free right now (a fixed pid-derived port collided once in a while)."""
+    with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as sk:
+        sk.bind(("127.0.0.1", 0))
+        return sk.getsockname()[1]
 
 
 def test_shard_images_covers_every_image_once():
@@ -32,7 +40,7 @@ def _worker(rank, world, port, q):
 def test_gloo_world2_max_and_gather():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + (os.getpid() % 2000)
+    port = _free_port()
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
@@ -70,7 +78,7 @@ def test_gloo_world2_mesh_gather_equals_single_process():
     """Per-image results after the sharded run + gather are identical to producing all images in one process."""
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 31500 + (os.getpid() % 2000)
+    port = _free_port()
     procs = [ctx.Process(target=_mesh_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
