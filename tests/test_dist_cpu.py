@@ -69,7 +69,9 @@ def _mesh_worker(rank, world, port, q):
         mine = D.shard_images(5, rank, world)
         got, nbytes = D.gather_meshes([_fake_mesh(i) for i in mine], mine, torch.device("cpu"))
         dist.barrier()
-        q.put((rank, {i: (v.clone(), f.clone()) for i, (v, f) in got.items()}, nbytes))
+        # numpy: pickled by value.  Tensors travel through an mp.Queue as file descriptors, which the parent can only
+        # receive while this process is alive -- it exits right after the put.
+        q.put((rank, {i: (v.numpy().copy(), f.numpy().copy()) for i, (v, f) in got.items()}, nbytes))
     finally:
         dist.destroy_process_group()
 
@@ -90,7 +92,8 @@ def test_gloo_world2_mesh_gather_equals_single_process():
     assert got1 == {} and sorted(got0) == [0, 1, 2, 3, 4]
     for i in range(5):
         v, f = _fake_mesh(i)
-        assert got0[i][0].dtype == v.dtype and torch.equal(got0[i][0], v) and torch.equal(got0[i][1], f)
+        gv, gf = torch.from_numpy(got0[i][0]), torch.from_numpy(got0[i][1])
+        assert gv.dtype == v.dtype and torch.equal(gv, v) and torch.equal(gf, f)
     assert b0 == b1 > 0                                      # bytes received on rank 0 == bytes sent by rank 1
     single, _ = D.gather_meshes([_fake_mesh(i) for i in range(5)], list(range(5)), torch.device("cpu"))
     assert sorted(single) == [0, 1, 2, 3, 4]
