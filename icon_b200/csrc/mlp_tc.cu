@@ -8,7 +8,7 @@
 // hi*Whi + hi*Wlo + lo*Whi with fp32 accumulation in tensor memory -- three kind::f16 MMAs per
 // k-step, fp32-class accuracy (parity bar 1e-4 on the logit; measured error in DESIGN.md).
 //
-// One persistent CTA per SM, 128 query points (= 128 TMEM lanes) per tile, 448 threads:
+// One persistent CTA per SM, 128 query points (= 128 TMEM lanes) per tile, 576 threads (18 warps):
 //   warp 0      weight producer: 1-D bulk copies (cp.async.bulk, TMA engine) of host-pre-swizzled
 //               K-major SWIZZLE_128B tiles from L2 into a 2 x 64 KB ring, mbarrier complete_tx
 //               (per tile: 8 layer-1 K-chunks and 2 pairs of layer-2 K-chunks; layer 0 and the x0 tail of
@@ -17,14 +17,18 @@
 //               (operands in uniform registers); the barriers of chunk j+1 are checked while chunk j still has
 //               MMAs to issue, so the tensor pipe never drains between chunks
 //   warps 2-9   workers, one TMEM lane (= query point) per thread, two threads per lane:
-//               per 64-column chunk of layer 0: tcgen05.ld -> +bias -> LeakyReLU -> hi/lo fp16 ->
-//               tcgen05.st as the A operand (in TMEM) of layer 1; same for layer 1 -> layer 2 (in 4
-//               K-chunks so layer 2 starts early).  They go straight on to the next tile.
+//               per 64-column chunk of layer 0: tcgen05.ld -> LeakyReLU -> hi/lo fp16 -> tcgen05.st as the A
+//               operand (in TMEM) of layer 1 (b0 is already in the accumulator: x0 column 15 is the constant 1 and
+//               row 15 of W0 holds b0); same with + b1 for layer 1 -> layer 2 (in 4 K-chunks so layer 2 starts
+//               early).  They go straight on to the next tile.
 //   warps 10-13 gather + epilogue, one query point per thread: the 16 input features of tile i+1 (bilinear /
 //               trilinear samples, SMPL record, outlier rule) are produced and published as the double-buffered
 //               x0 operand while tile i is in the tensor pipe; then layer 3 (141 -> 1) of tile i as an fp32 dot
-//               over the layer-2 accumulator, off the critical path of the next tile (which only waits until
-//               the accumulator has been read).
+//               over columns 0..63 of the layer-2 accumulator (b2 included, through the same constant-1 column
+//               in the x0 tail), off the critical path of the next tile (which only waits until the accumulator
+//               has been read); they sleep EPI_YIELD_NS after that read: the MMA warp and the next tile's first
+//               conversion need the issue slots more.
+//   warps 14-17 layer 3 over columns 64..127, partial sums handed to warps 10-13 through shared memory.
 // Layer-0 chunks are issued two ahead of the layer-1 chunk that consumes them, so the tensor pipe
 // always has queued work while the workers convert.  TMEM map (512 columns):
 //   [0,256) layer-1 accumulator (later [0,128) layer-2 accumulator)
@@ -43,7 +47,7 @@ constexpr int TC_THREADS = 576;      // 1 producer + 1 MMA + 8 worker + 4 gather
 constexpr int TC_M = 128;
 constexpr unsigned EPI_YIELD_NS = 1200;  // epilogue warps sleep this long after reading the layer-2 accumulator (measured: tools/mlp_timeline.py)
 
-// byte offsets inside the packed tensor-core weight blob (host: icon_b200/ops.py pack_mlp_tc)
+// byte offsets inside the packed tensor-core weight blob (host: icon_b200/ops.py pack_mlp)
 constexpr int TCB_W0 = 0;                         // hi 16384 | lo 16384, no swizzle, LBO 8192, SBO 128
 constexpr int TCB_W1 = 32768;                     // 8 x (hi 32768 | lo 32768), SW128, 256 rows x 64 k
 constexpr int TCB_W2 = TCB_W1 + 8 * 65536;        // 4 x (hi 16384 | lo 16384), SW128, 128 rows x 64 k
