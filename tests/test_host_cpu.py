@@ -79,6 +79,67 @@ def test_pack_mlp_folding_matches_oracle(built_lib, c0):
     assert (y - ref).abs().max() < 1e-5
 
 
+def _unswizzle128(buf, rows):
+    """Inverse of ops._img_sw128: K-major SWIZZLE_128B tile bytes -> [rows, 64] fp16."""
+    import numpy as np
+    t = np.frombuffer(buf, dtype=np.float16).reshape(rows, 8, 8)
+    out = np.zeros_like(t)
+    r = np.arange(rows)[:, None]
+    c = np.arange(8)[None, :]
+    out[r, c] = t[r, c ^ (r % 8)]
+    return out.reshape(rows, 64).astype(np.float64)
+
+
+def _unpack_nosw(buf, rows):
+    """Inverse of ops._img_nosw: [k-core][row group][8 rows][8 elems] -> [rows, 16] fp16."""
+    import numpy as np
+    t = np.frombuffer(buf, dtype=np.float16).reshape(2, rows // 8, 8, 8)
+    return np.ascontiguousarray(t.transpose(1, 2, 0, 3)).reshape(rows, 16).astype(np.float64)
+
+
+@pytest.mark.parametrize("c0", [13, 10])
+def test_tensor_core_blob_evaluated_like_the_kernel_matches_oracle(built_lib, c0):
+    """Decode the UMMA tiles of the tcgen05 blob (hi + lo) and run the network the way k_query_mlp_tc does: x0 column
+    15 is the constant 1, b0 and b2 are NOT added (they sit in row 15 of W0 and of the x0 tail of W2), b1 / b3 are."""
+    import numpy as np
+    from icon_b200 import ops
+    from oracle import query as OQ
+    sd = S.mlp_state_dict(c0, seed=9)
+    blob = ops.pack_mlp(sd, c0).tc.numpy().tobytes()
+    o = 0
+
+    def take(n):
+        nonlocal o
+        r = blob[o:o + n]
+        o += n
+        return r
+
+    W0 = _unpack_nosw(take(16384), 512) + _unpack_nosw(take(16384), 512)                       # [512, 16]
+    W1 = np.concatenate([_unswizzle128(take(32768), 256) + _unswizzle128(take(32768), 256) for _ in range(8)], 1)   # [256, 512]
+    W2 = np.concatenate([_unswizzle128(take(16384), 128) + _unswizzle128(take(16384), 128) for _ in range(4)], 1)   # [128, 256]
+    W2t = _unpack_nosw(take(4096), 128) + _unpack_nosw(take(4096), 128)                        # [128, 16]
+    f32 = np.frombuffer(take((512 + 256 + 128 + 144 + 4) * 4), dtype=np.float32).astype(np.float64)
+    assert o == ops.MLP_TC_BYTES
+    b1, w3, b3 = f32[512:768], f32[896:1040], f32[1040]
+    x = torch.randn(1, c0, 300, generator=torch.Generator().manual_seed(1)).double()
+    x16 = np.zeros((16, 300)); x16[:c0] = x[0].numpy(); x16[15] = 1.0
+    lre = lambda v: np.maximum(v, 0.01 * v)
+    h0 = lre(W0 @ x16)
+    h1 = lre(W1 @ h0 + b1[:, None])
+    h2 = lre(W2 @ h1 + W2t @ x16)
+    xs = x16.copy(); xs[15] = 0.0                                # layer 3 reads the fp32 feature copy: no constant row
+    y = w3[:128] @ h2 + w3[128:] @ xs + b3
+    ref = OQ.mlp_forward(sd, x, dtype=torch.float64)[0, 0].numpy()
+    assert np.abs(y - ref).max() < 2e-5                          # fp16 hi + lo weights: 22 significant bits
+
+
+def test_pack_mlp_refuses_16_input_channels(built_lib):
+    """x0 column 15 is taken by the constant that carries the folded biases."""
+    from icon_b200 import ops
+    with pytest.raises(NotImplementedError):
+        ops.pack_mlp(S.mlp_state_dict(16, seed=1), 16)
+
+
 def test_state_dict_keys_match_reference(golden_dir):
     from icon_b200 import config, net
     keys = json.load(open(os.path.join(golden_dir, "state_dict_keys.json")))
