@@ -50,7 +50,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         asm volatile("{\n.reg .pred q;\nmbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\nselp.b32 %0, 1, 0, q;\n}"
                      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
         if (done) break;
-        if (++spins > (1u << 27)) __trap();
+        if (++spins > (1u << 24)) __trap();
     }
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
