@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_query_mlp_tc(QueryParams q, c
     uint8_t *sm = smem_raw + (base - raw);
     float *x0f = reinterpret_cast<float *>(sm + SM_X0F);
     const float *sf32 = reinterpret_cast<const float *>(sm + SM_F32);
-    const float *sb0 = sf32, *sb1 = sf32 + 512, *sb2 = sf32 + 768, *sw3 = sf32 + 896, *sb3 = sf32 + 1040;
+    const float *sb1 = sf32 + 512, *sw3 = sf32 + 896, *sb3 = sf32 + 1040;     // b0 [0,512) and b2 [768,896) ride in the weight tiles
     float *spart = reinterpret_cast<float *>(sm + SM_PART);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sm + SM_MISC);
     const uint32_t bar0 = base + SM_BAR;
